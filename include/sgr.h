@@ -1,0 +1,156 @@
+/*
+ * sgr.h — C ABI of libsgr.so, the sm_100a StyleGAN2 synthesis path.
+ *
+ * Drop-in boundary.  The reference repo's native ABI for this path is two pybind11
+ * functions JIT-built by torch.utils.cpp_extension.load:
+ *     fused_bias_act(input, bias, refer, act, grad, alpha, scale)        libs/gan/StyleGAN2/op/fused_bias_act.cpp:14-24
+ *     upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0..y1)   libs/gan/StyleGAN2/op/upfirdn2d.cpp:16-26
+ * plus F.conv2d / F.conv_transpose2d(groups=batch) called from ModulatedConv2d.forward
+ * (libs/gan/StyleGAN2/model.py:232-273).  The entry points below replace all three.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); nothing is allocated here;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *   - return value: 0 on success, non-zero on error (sgr_last_error() gives a thread-local message);
+ *   - all tensors are fp32 unless stated; activations crossing this boundary are NCHW contiguous like the
+ *     reference's; the bf16 hi/lo "C8" layout is internal: [plane(hi,lo)][B][C/8][H][W][8] bf16.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef SGR_H_
+#define SGR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGR_MAX_STYLED 24
+#define SGR_MAX_RGB 12
+#define SGR_STYLE_DIM 512
+
+const char* sgr_version(void);
+const char* sgr_last_error(void);
+/* number of kernels of this library launched by the calling thread since the last reset (bench bookkeeping) */
+long long sgr_launch_count(void);
+void sgr_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * upfirdn2d: zero-insert upsample x`up`, pad (pad0 before / pad1 after, negative crops), true 2-D convolution
+ * with taps[kh][kw], decimate x`down`.  Replaces op/upfirdn2d.cpp:16-26 + op/upfirdn2d_kernel.cu:52-272
+ * (same factors on both axes, as every call site in model.py uses).  x: [planes,in_h,in_w], y: [planes,out_h,out_w]
+ * with out = (in*up + pad0 + pad1 - k + down) / down  (op/upfirdn2d.py:104-105).
+ */
+int sgr_upfirdn2d(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int up, int down,
+                  int pad0, int pad1, int kh, int kw, void* stream);
+
+/* fused bias + leaky-relu * scale.  Replaces op/fused_bias_act.cpp:14-24 / fused_bias_act_kernel.cu:18-99.
+ * grad == 0: y = lrelu(x + bias[c], slope) * scale          (act*10+grad == 30; bias may be NULL)
+ * grad == 1: y = (ref > 0 ? x : slope * x) * scale           (== 31; `ref` is the saved forward OUTPUT)
+ * x: [outer, channels, inner] contiguous. */
+int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
+                       long long inner, int grad, float slope, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Weight packing for the tcgen05 implicit-GEMM convolution.
+ * weight: [cout, cin, k, k] fp32 (the reference parameter ModulatedConv2d.weight[0], model.py:216-218), k = 3 or 1.
+ * up != 0: the stride-2 transposed conv + 4x4 FIR of model.py:246-257 is folded into four 3x3 phase kernels
+ *          (W (*) fir, 6x6); fir = the layer's blur.kernel buffer [4,4].
+ * transpose != 0 packs the adjoint (data-gradient) operator instead: GEMM columns = cin, K = cout (x4 for up).
+ * packed: bf16 hi/lo slabs in shared-memory image order, sgr_packed_weight_bytes() bytes.
+ * wsq:    [cout, cin] fp32 = sum_k (weight*scale)^2 for the demodulation mini-GEMM (may be NULL).
+ */
+size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose);
+int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up,
+                            int transpose, void* packed, float* wsq, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Layout helpers (module-level calls and tests; the fused network path never needs them).
+ * NCHW fp32 (optionally * scale[b,c]) -> C8 bf16 hi/lo planes; s2d != 0 additionally folds 2x2 pixel phases
+ * into channels (channel = phase*C + c at half resolution), the layout the up-layer adjoint consumes. */
+int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, int channels, int h, int w, int s2d,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * One modulated convolution (ModulatedConv2d.forward + NoiseInjection + FusedLeakyReLU, model.py:232-287,331-337)
+ * on tensor cores.  Input is C8 hi/lo planes ALREADY multiplied by the style s[b,cin] (the modulation of
+ * model.py:235-236 moved from the weights to the activations).
+ *   z   = conv(x_c8, W) (3x3 pad 1 | 1x1 | polyphase up)            fp32 accumulate of bf16x3 products
+ *   t   = z * demod[b,o] + noise_weight[0] * noise[y,x] + bias[o]    (each term optional: NULL pointer skips it)
+ *   t   = act ? max(t, 0.2 t) : t
+ *   out_f32[b,o,y,x]  = t * act_gain                                  (optional, NCHW fp32)
+ *   out_c8            = split_bf16(t * (s2 ? s2[b,o] : act_gain))     (optional, next layer's input)
+ *   rgb_acc[b,c,y,x] += sum_o t * rgb_coef[b,c,o]                     (optional fused ToRGB, atomic)
+ */
+typedef struct sgr_conv_args {
+  int batch, cin, cout, h_in, w_in;
+  int ksize;              /* 3 or 1 */
+  int up;                 /* 0: same resolution; 1: output is 2x (polyphase), cout phases packed by sgr_pack_modconv_weight */
+  int act;                /* apply leaky-relu 0.2 */
+  float act_gain;         /* sqrt(2) for StyledConv, 1 for raw conv */
+  const void* x_c8;       /* [2][B][cin/8][h_in][w_in][8] bf16 */
+  const void* w_packed;
+  const float* demod;     /* [B,cout] or NULL */
+  const float* bias;      /* [cout] or NULL */
+  const float* noise;     /* [h_out,w_out] (or [B,h_out,w_out] with noise_batch_stride = h_out*w_out) or NULL */
+  long long noise_batch_stride; /* elements between samples' noise maps; 0 = shared (registered buffer) */
+  const float* noise_weight; /* [1] device scalar (required when noise != NULL) */
+  const float* s2;        /* [B,cout] or NULL */
+  void* out_c8;           /* or NULL */
+  float* out_f32;         /* or NULL */
+  const float* rgb_coef;  /* [B,3,cout] or NULL */
+  float* rgb_acc;         /* [B,3,h_out,w_out], must be zero-initialised by the caller */
+} sgr_conv_args;
+int sgr_modconv_forward(const sgr_conv_args* args, void* stream);
+
+/* styles s[b,i] = latent_row[b,:] . mod_weight[i,:] / sqrt(512) + mod_bias[i]   (EqualLinear, model.py:148-157,235)
+ * demod d[b,o]  = rsqrt(sum_i s[b,i]^2 wsq[o,i] + 1e-8)                          (model.py:238-240 in the form of §9.1) */
+int sgr_style_affine(const float* latent, int latent_stride, int batch, const float* mod_weight,
+                     const float* mod_bias, int cin, float* s_out, void* stream);
+int sgr_demod(const float* s, const float* wsq, int batch, int cin, int cout, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole synthesis network (Generator.forward after the mapping/truncation glue, model.py:519-534).
+ */
+typedef struct sgr_styled_layer {
+  int cin, cout, up, latent_row;
+  const void* w_packed;      /* forward operator, sgr_pack_modconv_weight(transpose=0) */
+  const float* wsq;          /* [cout,cin] */
+  const float* mod_weight;   /* [cin,512] */
+  const float* mod_bias;     /* [cin] */
+  const float* noise;        /* [res,res], or [B,res,res] when noise_batch_stride != 0 */
+  long long noise_batch_stride;
+  const float* noise_weight; /* [1] */
+  const float* act_bias;     /* [cout] */
+} sgr_styled_layer;
+
+typedef struct sgr_rgb_layer {
+  int cin, latent_row;
+  const float* weight;       /* [3,cin] (ToRGB.conv.weight[0,:,:,0,0]) */
+  const float* mod_weight;   /* [cin,512] */
+  const float* mod_bias;     /* [cin] */
+  const float* bias;         /* [3] */
+  const float* fir;          /* upsample.kernel [4,4] (NULL for to_rgb1) */
+} sgr_rgb_layer;
+
+typedef struct sgr_synthesis {
+  int size;                  /* output resolution, power of two >= 8 */
+  int n_styled;              /* conv1 + convs.* = 2*log2(size) - 3 */
+  int n_rgb;                 /* to_rgb1 + to_rgbs.* = log2(size) - 1 */
+  int n_latent;
+  const float* const_input;  /* [512,4,4] */
+  sgr_styled_layer styled[SGR_MAX_STYLED];
+  sgr_rgb_layer rgb[SGR_MAX_RGB];
+} sgr_synthesis;
+
+size_t sgr_synthesis_workspace_bytes(const sgr_synthesis* net, int batch);
+/* latent: [B,n_latent,512] (already truncated / shifted); image: [B,3,size,size] fp32 NCHW.
+ * feats: NULL, or n_styled device pointers (entries may be NULL) receiving each StyledConv output [B,cout,res,res]. */
+int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
+                          size_t workspace_bytes, float* const* feats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGR_H_ */

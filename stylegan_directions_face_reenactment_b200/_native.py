@@ -1,0 +1,95 @@
+"""ctypes binding of libsgr.so (include/sgr.h).  There is no CPU fallback: if the library is missing or a call fails,
+a RuntimeError is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsgr.so')
+
+MAX_STYLED = 24
+MAX_RGB = 12
+STYLE_DIM = 512
+
+_fp = C.c_void_p          # device pointers travel as integers
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [('batch', C.c_int), ('cin', C.c_int), ('cout', C.c_int), ('h_in', C.c_int), ('w_in', C.c_int),
+                ('ksize', C.c_int), ('up', C.c_int), ('act', C.c_int), ('act_gain', C.c_float),
+                ('x_c8', _fp), ('w_packed', _fp), ('demod', _fp), ('bias', _fp), ('noise', _fp),
+                ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('s2', _fp), ('out_c8', _fp),
+                ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_acc', _fp)]
+
+
+class StyledLayer(C.Structure):
+    _fields_ = [('cin', C.c_int), ('cout', C.c_int), ('up', C.c_int), ('latent_row', C.c_int),
+                ('w_packed', _fp), ('wsq', _fp), ('mod_weight', _fp), ('mod_bias', _fp), ('noise', _fp),
+                ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('act_bias', _fp)]
+
+
+class RgbLayer(C.Structure):
+    _fields_ = [('cin', C.c_int), ('latent_row', C.c_int), ('weight', _fp), ('mod_weight', _fp), ('mod_bias', _fp),
+                ('bias', _fp), ('fir', _fp)]
+
+
+class Synthesis(C.Structure):
+    _fields_ = [('size', C.c_int), ('n_styled', C.c_int), ('n_rgb', C.c_int), ('n_latent', C.c_int),
+                ('const_input', _fp), ('styled', StyledLayer * MAX_STYLED), ('rgb', RgbLayer * MAX_RGB)]
+
+
+# name -> (restype, argtypes); mirrors include/sgr.h one to one (tests check every symbol is exported)
+SIGNATURES = {
+    'sgr_version': (C.c_char_p, []),
+    'sgr_last_error': (C.c_char_p, []),
+    'sgr_launch_count': (C.c_longlong, []),
+    'sgr_reset_launch_count': (None, []),
+    'sgr_upfirdn2d': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 9 + [_fp]),
+    'sgr_fused_bias_act': (C.c_int, [_fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_float,
+                                     C.c_float, _fp]),
+    'sgr_packed_weight_bytes': (C.c_size_t, [C.c_int] * 5),
+    'sgr_pack_modconv_weight': (C.c_int, [_fp, _fp] + [C.c_int] * 5 + [_fp, _fp, _fp]),
+    'sgr_nchw_to_c8': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 5 + [_fp]),
+    'sgr_modconv_forward': (C.c_int, [C.POINTER(ConvArgs), _fp]),
+    'sgr_style_affine': (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp]),
+    'sgr_demod': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    'sgr_synthesis_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
+    'sgr_synthesis_forward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, _fp, _fp, C.c_size_t, C.POINTER(_fp),
+                                        _fp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsgr.so once.  Raises if it has not been built (python __graft_entry__.py / make -C csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('libsgr.so is not built (%s); run `make -C %s` — there is no CPU fallback'
+                               % (LIB_PATH, os.path.join(_HERE, 'csrc')))
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError('%s failed: %s' % (what, lib().sgr_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('libsgr needs CUDA tensors (got %s): there is no CPU fallback' % t.device)
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,426 @@
+// Modulated convolution as an implicit GEMM on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces, for one layer, the whole chain of the reference's ModulatedConv2d.forward -> NoiseInjection ->
+// FusedLeakyReLU (libs/gan/StyleGAN2/model.py:232-287,331-337, op/fused_bias_act_kernel.cu:18-49) and, for the
+// upsampling layers, conv_transpose2d + Blur/upfirdn2d (model.py:246-257, op/upfirdn2d_kernel.cu:52-137), and
+// optionally the following ToRGB 1x1 modulated conv (model.py:350-354).
+//
+// GEMM view:  D[m, n] = sum_{tap, i} A_tap[m, i] * Wp[n, tap, i]
+//   m : 128 pixels of a (bw x bh x bb) box of the INPUT-resolution grid (TMEM lane = pixel)
+//   n : output channel (plain) or phase*cout + channel (polyphase up-conv: 4 output pixels per input pixel)
+//   A : activations already multiplied by the per-sample style, stored as bf16 hi/lo planes in the "C8" layout
+//       [plane][B][C/8][H][W][8]; each 3x3 tap is one TMA box load at shifted coordinates (zero OOB fill = padding)
+//   Wp: batch-shared weights, pre-split into bf16 hi/lo and pre-arranged in the shared-memory image order, so a
+//       stage's weight slab is one 1-D bulk copy.
+// fp32 parity needs more than one bf16 pass: every K step issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (bf16x3).
+//
+// Shared-memory operand layout (no swizzle, K-major): [plane][chunk of 8 channels][row][8 bf16]; a row is 16 B,
+// rows are contiguous (SBO = 128 B per 8 rows), K chunks are LBO = rows*16 B apart.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
+// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/style/ToRGB -> HBM).
+// The accumulator is double-buffered in TMEM (2 x NT columns) so the epilogue of tile t overlaps the MMAs of t+1.
+#include <algorithm>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+
+namespace sgr {
+
+template <int NT>
+struct ConvCfg {
+  static constexpr int kBBytes = NT * kBlockK * 2 * 2;                 // hi + lo planes of one weight stage
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes;
+};
+
+struct TileCoord {
+  int n_tile, tx, ty, tb;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile / p.m_tiles;
+  int m = tile - t.n_tile * p.m_tiles;
+  t.tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  t.ty = m % p.tiles_y;
+  t.tb = m / p.tiles_y;
+  return t;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                         const ConvKernelParams p) {
+  using Cfg = ConvCfg<NT>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_base = smem + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int x0 = tc.tx * p.bw, y0 = tc.ty * p.bh, b0 = tc.tb * p.bb;
+        const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const uint32_t s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = stage_base + s * Cfg::kStageBytes;
+            mbar_expect_tx(&full[s], Cfg::kStageBytes);
+            tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
+            bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(tap * p.kchunks + kc) * (NT * 64), Cfg::kBBytes,
+                     &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, NT);
+      constexpr uint32_t kALbo = kTileM * 16, kBLbo = NT * 16;
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * NT;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const uint32_t s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int j = 0; j < kBlockK / 16; ++j) {
+            const uint64_t a_hi = umma_desc(a_addr + j * 2 * kALbo, kALbo, 128);
+            const uint64_t a_lo = umma_desc(a_addr + kABytes / 2 + j * 2 * kALbo, kALbo, 128);
+            const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
+            const uint64_t b_lo = umma_desc(b_addr + Cfg::kBBytes / 2 + j * 2 * kBLbo, kBLbo, 128);
+            umma_bf16(d_tmem, a_lo, b_hi, idesc, (k | j) != 0);
+            umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+            umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tfull[as]);       // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int ew = warp - 4;                       // == warp % 4: the TMEM lane quarter this warp may access
+    const int r = ew * 32 + lane;                  // tile row == pixel
+    const int xx = r % p.bw;
+    const int yy = (r / p.bw) % p.bh;
+    const int bl = r / (p.bw * p.bh);
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    const size_t plane_stride = static_cast<size_t>(p.B) * p.cout * p.Hout * p.Wout;   // elements per C8 plane
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int b = tc.tb * p.bb + bl;
+      const int y = tc.ty * p.bh + yy;
+      const int x = tc.tx * p.bw + xx;
+      const bool valid = b < p.B;
+      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * NT + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int n0 = tc.n_tile * NT + c;
+          const int phase = p.up ? n0 / p.cout : 0;
+          const int o0 = n0 & (p.cout - 1);
+          const int oy = p.up ? 2 * y + (phase >> 1) : y;
+          const int ox = p.up ? 2 * x + (phase & 1) : x;
+          const float nz = p.noise ? nw * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride + oy * p.Wout + ox) : 0.f;
+          const float* dptr = p.demod ? p.demod + static_cast<size_t>(b) * p.cout + o0 : nullptr;
+          const float* bptr = p.bias ? p.bias + o0 : nullptr;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 d4 = dptr ? __ldg(reinterpret_cast<const float4*>(dptr) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 b4 = bptr ? __ldg(reinterpret_cast<const float4*>(bptr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float t0 = fmaf(v[4 * q + 0], d4.x, nz + b4.x);
+            float t1 = fmaf(v[4 * q + 1], d4.y, nz + b4.y);
+            float t2 = fmaf(v[4 * q + 2], d4.z, nz + b4.z);
+            float t3 = fmaf(v[4 * q + 3], d4.w, nz + b4.w);
+            if (p.act) {
+              t0 = fmaxf(t0, 0.2f * t0);
+              t1 = fmaxf(t1, 0.2f * t1);
+              t2 = fmaxf(t2, 0.2f * t2);
+              t3 = fmaxf(t3, 0.2f * t3);
+            }
+            v[4 * q + 0] = t0;
+            v[4 * q + 1] = t1;
+            v[4 * q + 2] = t2;
+            v[4 * q + 3] = t3;
+          }
+          if (p.rgb_coef) {
+            const float* cptr = p.rgb_coef + static_cast<size_t>(b) * 3 * p.cout + o0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(cptr) + q);
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(cptr + p.cout) + q);
+              const float4 c2 = __ldg(reinterpret_cast<const float4*>(cptr + 2 * p.cout) + q);
+              rgb0 = fmaf(v[4 * q], c0.x, fmaf(v[4 * q + 1], c0.y, fmaf(v[4 * q + 2], c0.z, fmaf(v[4 * q + 3], c0.w, rgb0))));
+              rgb1 = fmaf(v[4 * q], c1.x, fmaf(v[4 * q + 1], c1.y, fmaf(v[4 * q + 2], c1.z, fmaf(v[4 * q + 3], c1.w, rgb1))));
+              rgb2 = fmaf(v[4 * q], c2.x, fmaf(v[4 * q + 1], c2.y, fmaf(v[4 * q + 2], c2.z, fmaf(v[4 * q + 3], c2.w, rgb2))));
+            }
+          }
+          if (p.out_f32) {
+            float* optr = p.out_f32 + ((static_cast<size_t>(b) * p.cout + o0) * p.Hout + oy) * p.Wout + ox;
+            const size_t cs = static_cast<size_t>(p.Hout) * p.Wout;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) optr[j * cs] = v[j] * p.act_gain;
+          }
+          if (p.out_c8) {
+            const float* sptr = p.s2 ? p.s2 + static_cast<size_t>(b) * p.cout + o0 : nullptr;
+            // element offset of channel chunk (o0/8) of this pixel inside the hi plane
+            __nv_bfloat16* optr = p.out_c8 +
+                (((static_cast<size_t>(b) * (p.cout >> 3) + (o0 >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
+            const size_t chunk_stride = static_cast<size_t>(p.Hout) * p.Wout * 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float g[8];
+              if (sptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sptr) + 2 * q);
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sptr) + 2 * q + 1);
+                g[0] = s0.x; g[1] = s0.y; g[2] = s0.z; g[3] = s0.w;
+                g[4] = s1.x; g[5] = s1.y; g[6] = s1.z; g[7] = s1.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] = p.act_gain;
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[8 * q + 2 * e] * g[2 * e], h0, l0);
+                split_bf16(v[8 * q + 2 * e + 1] * g[2 * e + 1], h1, l1);
+                hi[e] = pack_bf16x2(h0, h1);
+                lo[e] = pack_bf16x2(l0, l1);
+              }
+              *reinterpret_cast<uint4*>(optr + q * chunk_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(optr + plane_stride + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);     // 128 arrivals release the accumulator buffer
+      if (valid && p.rgb_coef) {
+        float* rptr = p.rgb_acc + ((static_cast<size_t>(b) * 3) * p.Hout + y) * p.Wout + x;
+        const size_t cs = static_cast<size_t>(p.Hout) * p.Wout;
+        atomicAdd(rptr, rgb0);
+        atomicAdd(rptr + cs, rgb1);
+        atomicAdd(rptr + 2 * cs, rgb2);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+template <int NT>
+static int launch_nt(const ConvKernelParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(modconv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<NT>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("modconv: cudaFuncSetAttribute(smem=%d) failed: %s", ConvCfg<NT>::kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  const int sms = num_sms();
+  if (sms <= 0) {
+    set_error("modconv: no CUDA device");
+    return 1;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = std::min(total, sms);
+  modconv_kernel<NT><<<grid, 256, ConvCfg<NT>::kSmemBytes, stream>>>(tmap, p);
+  count_launch();
+  return check_launch("modconv_kernel") ? 0 : 1;
+}
+
+int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream) {
+  switch (nt) {
+    case 256: return launch_nt<256>(p, tmap, stream);
+    case 128: return launch_nt<128>(p, tmap, stream);
+    case 64: return launch_nt<64>(p, tmap, stream);
+    case 32: return launch_nt<32>(p, tmap, stream);
+    default: set_error("modconv: unsupported column tile %d", nt); return 1;
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
+                        int bb) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  const cuuint64_t chunk_bytes = static_cast<cuuint64_t>(h) * w * 16;
+  const cuuint64_t dims[5] = {static_cast<cuuint64_t>(w) * 8, static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch),
+                              static_cast<cuuint64_t>(channels / 8), 2};
+  const cuuint64_t strides[4] = {static_cast<cuuint64_t>(w) * 16, chunk_bytes * (channels / 8), chunk_bytes,
+                                 chunk_bytes * (channels / 8) * batch};
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(bw * 8), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bb),
+                             kBlockK / 8, 2};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for B=%d C=%d H=%d W=%d box=%dx%dx%d", static_cast<int>(r), batch,
+              channels, h, w, bw, bh, bb);
+    return 1;
+  }
+  return 0;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
+  if (!a || !a->x_c8 || !a->w_packed) {
+    set_error("modconv: null input");
+    return 1;
+  }
+  if (a->batch <= 0 || !is_pow2(a->h_in) || !is_pow2(a->w_in) || a->h_in < 4 || a->w_in < 4) {
+    set_error("modconv: unsupported geometry B=%d H=%d W=%d (power-of-two sizes >= 4)", a->batch, a->h_in, a->w_in);
+    return 1;
+  }
+  if (a->cin % kBlockK != 0 || !is_pow2(a->cout) || a->cout < 32 || (a->ksize != 3 && a->ksize != 1)) {
+    set_error("modconv: unsupported channels cin=%d cout=%d k=%d (cin %% 32 == 0, cout power of two >= 32)", a->cin,
+              a->cout, a->ksize);
+    return 1;
+  }
+  if (a->up && a->ksize != 3) {
+    set_error("modconv: up requires ksize 3");
+    return 1;
+  }
+  if (a->noise && !a->noise_weight) {
+    set_error("modconv: noise without noise_weight");
+    return 1;
+  }
+  if (a->rgb_coef && (!a->rgb_acc || a->up)) {
+    set_error("modconv: fused ToRGB needs rgb_acc and a non-upsampling layer");
+    return 1;
+  }
+  p->B = a->batch;
+  p->H = a->h_in;
+  p->W = a->w_in;
+  p->bw = std::min(a->w_in, 16);
+  p->bh = std::min(a->h_in, kTileM / p->bw);
+  p->bb = kTileM / (p->bw * p->bh);
+  p->tiles_x = a->w_in / p->bw;
+  p->tiles_y = a->h_in / p->bh;
+  p->tiles_b = (a->batch + p->bb - 1) / p->bb;
+  p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
+  const int n_total = a->cout * (a->up ? 4 : 1);
+  *nt = pick_nt(n_total);
+  p->n_tiles = n_total / *nt;
+  p->kchunks = a->cin / kBlockK;
+  p->ntaps = a->ksize * a->ksize;
+  p->cout = a->cout;
+  p->up = a->up ? 1 : 0;
+  p->Hout = a->up ? 2 * a->h_in : a->h_in;
+  p->Wout = a->up ? 2 * a->w_in : a->w_in;
+  p->act = a->act;
+  p->act_gain = a->act_gain;
+  p->wpacked = static_cast<const __nv_bfloat16*>(a->w_packed);
+  p->demod = a->demod;
+  p->bias = a->bias;
+  p->noise = a->noise;
+  p->noise_w = a->noise_weight;
+  p->noise_bstride = a->noise_batch_stride;
+  p->s2 = a->s2;
+  p->out_c8 = static_cast<__nv_bfloat16*>(a->out_c8);
+  p->out_f32 = a->out_f32;
+  p->rgb_coef = a->rgb_coef;
+  p->rgb_acc = a->rgb_acc;
+  return 0;
+}
+
+}  // namespace sgr

@@ -1,0 +1,313 @@
+// Small HBM/latency-bound kernels around the tensor-core convolution:
+//   weight packing (fp32 -> bf16 hi/lo slabs, polyphase folding of conv_transpose2d + FIR), per-sample styles
+//   (EqualLinear modulation), demodulation coefficients, epilogue tables, constant input, layout conversion.
+#include <math.h>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+
+namespace sgr {
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// Effective kernel value for GEMM column n / reduction index (tap, i).
+//   plain:      Wp[o][tap=(ky,kx)][i] = scale * W[o][i][ky][kx]                         (F.conv2d, model.py:269)
+//   up:         Wp[phase*cout+o][tap=(ty,tx)][i] = Kc[o][i][py+2-2dy][px+2-2dx],  Kc = (scale*W) (*) fir (6x6 full conv)
+//               reproduces conv_transpose2d(stride 2) followed by upfirdn2d(pad=(1,1))   (model.py:254-257)
+//   transpose:  the adjoint operators (data gradient): columns = cin, reduction over (tap, cout[*4 phases]).
+__device__ float effective_weight(const float* __restrict__ w, const float* __restrict__ fir, int cout, int cin,
+                                  int ks, int up, int transpose, float scale, int n, int tap, int kidx) {
+  const int dy = ks == 3 ? tap / 3 - 1 : 0;
+  const int dx = ks == 3 ? tap % 3 - 1 : 0;
+  if (!transpose) {
+    if (!up) {
+      return scale * w[((static_cast<size_t>(n) * cin + kidx) * ks + (dy + ks / 2)) * ks + (dx + ks / 2)];
+    }
+    const int phase = n / cout, o = n % cout;
+    const int a = (phase >> 1) + 2 - 2 * dy, b = (phase & 1) + 2 - 2 * dx;   // index into the 6x6 merged kernel
+    float acc = 0.f;
+    const float* wk = w + (static_cast<size_t>(o) * cin + kidx) * 9;
+    for (int u = 0; u < 3; ++u)
+      for (int v = 0; v < 3; ++v) {
+        const int fa = a - u, fb = b - v;
+        if (fa >= 0 && fa < 4 && fb >= 0 && fb < 4) acc += scale * wk[u * 3 + v] * fir[fa * 4 + fb];
+      }
+    return acc;
+  }
+  // adjoint: column n = input channel i; reduction index = (phase,) output channel o; tap offsets negate.
+  if (!up) {
+    const int o = kidx;
+    return scale * w[((static_cast<size_t>(o) * cin + n) * ks + (ks / 2 - dy)) * ks + (ks / 2 - dx)];
+  }
+  const int phase = kidx / cout, o = kidx % cout;
+  // forward: y[2m+py] += Kc[py+2-2d] x[m+d]  =>  gx[m'] = sum_d Kc[py+2-2d] gy_phase[m'-d]; as a correlation with
+  // offset e = -d reading gy_phase[m'+e]: Kc index = py+2+2e.
+  const int a = (phase >> 1) + 2 + 2 * dy, b = (phase & 1) + 2 + 2 * dx;
+  float acc = 0.f;
+  const float* wk = w + (static_cast<size_t>(o) * cin + n) * 9;
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) {
+      const int fa = a - u, fb = b - v;
+      if (fa >= 0 && fa < 4 && fb >= 0 && fb < 4) acc += scale * wk[u * 3 + v] * fir[fa * 4 + fb];
+    }
+  return acc;
+}
+
+// One thread per 8-element (16 B) row of the packed image; writes the hi and the lo plane entry.
+// packed layout: [n_tile][tap][kc][plane][chunk(4)][n_local(NT)][8]
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ fir, int cout, int cin,
+                                   int ks, int up, int transpose, int n_total, int k_total, int nt, float scale,
+                                   __nv_bfloat16* __restrict__ packed) {
+  const int ntaps = ks * ks;
+  const int kchunks = k_total / kBlockK;
+  const long long rows = static_cast<long long>(n_total / nt) * ntaps * kchunks * 4 * nt;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows) return;
+  long long t = idx;
+  const int nl = static_cast<int>(t % nt); t /= nt;
+  const int chunk = static_cast<int>(t % 4); t /= 4;
+  const int kc = static_cast<int>(t % kchunks); t /= kchunks;
+  const int tap = static_cast<int>(t % ntaps); t /= ntaps;
+  const int ntile = static_cast<int>(t);
+  const int n = ntile * nt + nl;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k0 = kc * kBlockK + chunk * 8 + 2 * e;
+    const float v0 = effective_weight(w, fir, cout, cin, ks, up, transpose, scale, n, tap, k0);
+    const float v1 = effective_weight(w, fir, cout, cin, ks, up, transpose, scale, n, tap, k0 + 1);
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    hi[e] = pack_bf16x2(h0, h1);
+    lo[e] = pack_bf16x2(l0, l1);
+  }
+  const size_t slab = (static_cast<size_t>(ntile) * ntaps + tap) * kchunks + kc;        // stage index
+  const size_t row_in_plane = static_cast<size_t>(chunk) * nt + nl;
+  uint4* dst = reinterpret_cast<uint4*>(packed) + slab * (2 * 4 * nt);
+  dst[row_in_plane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  dst[4 * nt + row_in_plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void wsq_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, float scale,
+                           float* __restrict__ wsq) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * cin) return;
+  const float* wk = w + static_cast<size_t>(idx) * ntaps;
+  float acc = 0.f;
+  for (int t = 0; t < ntaps; ++t) {
+    const float v = scale * wk[t];
+    acc = fmaf(v, v, acc);
+  }
+  wsq[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ styles
+
+// One warp per (job, i): s[b,i] = <latent[b,row,:], W[i,:]> / sqrt(512) + bias[i]   (model.py:148-157 with lr_mul = 1)
+__global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ latent, int latent_stride, int batch) {
+  const StyleJob& j = jobs.job[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= j.cin) return;
+  const float4* wrow = reinterpret_cast<const float4*>(j.mod_weight + static_cast<size_t>(i) * SGR_STYLE_DIM);
+  float4 wv[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) wv[q] = __ldg(wrow + q * 32 + lane);
+  const float bias = __ldg(j.mod_bias + i);
+  const float scale = 0.044194173824159216f;   // 1/sqrt(512)
+  for (int b = 0; b < batch; ++b) {
+    const float4* lrow = reinterpret_cast<const float4*>(latent + static_cast<size_t>(b) * latent_stride +
+                                                         static_cast<size_t>(j.latent_row) * SGR_STYLE_DIM);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 l = __ldg(lrow + q * 32 + lane);
+      acc = fmaf(l.x, wv[q].x, fmaf(l.y, wv[q].y, fmaf(l.z, wv[q].z, fmaf(l.w, wv[q].w, acc))));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) j.out[static_cast<size_t>(b) * j.cin + i] = fmaf(acc, scale, bias);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ demod + tables
+
+// One warp per (job, b, o).
+__global__ void table_kernel(const TableJobs jobs, int batch) {
+  const TableJob& j = jobs.job[blockIdx.z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int b = blockIdx.y;
+  if (o >= j.cout) return;
+  const float* s = j.s + static_cast<size_t>(b) * j.cin;
+  const float* q = j.wsq + static_cast<size_t>(o) * j.cin;
+  float acc = 0.f;
+  for (int i = lane; i < j.cin; i += 32) {
+    const float sv = __ldg(s + i);
+    acc = fmaf(sv * sv, __ldg(q + i), acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const float kSqrt2 = 1.4142135623730951f;
+    j.demod[static_cast<size_t>(b) * j.cout + o] = rsqrtf(acc + 1e-8f);
+    if (j.s_next) j.s2[static_cast<size_t>(b) * j.cout + o] = kSqrt2 * __ldg(j.s_next + static_cast<size_t>(b) * j.cout + o);
+    if (j.s_rgb) {
+      const float sr = kSqrt2 * __ldg(j.s_rgb + static_cast<size_t>(b) * j.cout + o) * rsqrtf(static_cast<float>(j.cout));
+      for (int c = 0; c < 3; ++c)
+        j.rgb_coef[(static_cast<size_t>(b) * 3 + c) * j.cout + o] = sr * __ldg(j.w_rgb + c * j.cout + o);
+    }
+  }
+}
+
+__global__ void demod_kernel(const float* __restrict__ s, const float* __restrict__ wsq, int cin, int cout,
+                             float* __restrict__ d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int b = blockIdx.y;
+  if (o >= cout) return;
+  float acc = 0.f;
+  for (int i = lane; i < cin; i += 32) {
+    const float sv = __ldg(s + static_cast<size_t>(b) * cin + i);
+    acc = fmaf(sv * sv, __ldg(wsq + static_cast<size_t>(o) * cin + i), acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) d[static_cast<size_t>(b) * cout + o] = rsqrtf(acc + 1e-8f);
+}
+
+// ------------------------------------------------------------------------------------------------ layout conversion
+// NCHW fp32 (* scale[b,c]) -> C8 hi/lo planes.  One thread per (b, chunk, y, x) writes 16 B to each plane.
+// s2d: channel' = phase*C + c at (y/2, x/2), phase = (y&1)*2 + (x&1).
+__global__ void nchw_to_c8_kernel(const float* __restrict__ x, const float* __restrict__ scale, int batch, int C, int H,
+                                  int W, int s2d, __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(batch) * (C / 8) * H * W;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  long long t = idx;
+  const int xx = static_cast<int>(t % W); t /= W;
+  const int yy = static_cast<int>(t % H); t /= H;
+  const int ch = static_cast<int>(t % (C / 8)); t /= (C / 8);
+  const int b = static_cast<int>(t);
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = ch * 8 + 2 * e + h;
+      float val = __ldg(x + ((static_cast<size_t>(b) * C + c) * H + yy) * W + xx);
+      if (scale) val *= __ldg(scale + static_cast<size_t>(b) * C + c);
+      v[h] = val;
+    }
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[0], h0, l0);
+    split_bf16(v[1], h1, l1);
+    hi[e] = pack_bf16x2(h0, h1);
+    lo[e] = pack_bf16x2(l0, l1);
+  }
+  size_t off, plane;
+  if (!s2d) {
+    off = ((static_cast<size_t>(b) * (C / 8) + ch) * H + yy) * W + xx;
+    plane = static_cast<size_t>(batch) * (C / 8) * H * W;
+  } else {
+    const int phase = (yy & 1) * 2 + (xx & 1);
+    const int H2 = H / 2, W2 = W / 2, C4 = 4 * C;
+    off = ((static_cast<size_t>(b) * (C4 / 8) + phase * (C / 8) + ch) * H2 + (yy >> 1)) * W2 + (xx >> 1);
+    plane = static_cast<size_t>(batch) * (C4 / 8) * H2 * W2;
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  o4[off] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  o4[plane + off] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ConstantInput (model.py:290-300) times the first layer's style, straight into C8 planes.
+__global__ void const_input_kernel(const float* __restrict__ cinput, const float* __restrict__ s, int batch, int C,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int total = batch * (C / 8) * 16;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int pix = idx % 16;
+  const int ch = (idx / 16) % (C / 8);
+  const int b = idx / (16 * (C / 8));
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = ch * 8 + 2 * e;
+    const float v0 = __ldg(cinput + c * 16 + pix) * __ldg(s + static_cast<size_t>(b) * C + c);
+    const float v1 = __ldg(cinput + (c + 1) * 16 + pix) * __ldg(s + static_cast<size_t>(b) * C + c + 1);
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    hi[e] = pack_bf16x2(h0, h1);
+    lo[e] = pack_bf16x2(l0, l1);
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  o4[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  o4[static_cast<size_t>(total) + idx] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------------------------------------ host wrappers
+int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose,
+                       void* packed, float* wsq, cudaStream_t st) {
+  const int n_total = transpose ? cin : cout * (up ? 4 : 1);
+  const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
+  const int nt = pick_nt(n_total);
+  const float scale = 1.f / sqrtf(static_cast<float>(cin) * ks * ks);
+  const long long rows = static_cast<long long>(n_total) * ks * ks * (k_total / 8);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((rows + threads - 1) / threads);
+  pack_weight_kernel<<<blocks, threads, 0, st>>>(w, fir, cout, cin, ks, up, transpose, n_total, k_total, nt, scale,
+                                                 static_cast<__nv_bfloat16*>(packed));
+  count_launch();
+  if (!check_launch("pack_weight_kernel")) return 1;
+  if (wsq) {
+    wsq_kernel<<<(cout * cin + 255) / 256, 256, 0, st>>>(w, cout, cin, ks * ks, scale, wsq);
+    count_launch();
+    if (!check_launch("wsq_kernel")) return 1;
+  }
+  return 0;
+}
+
+int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st) {
+  int cmax = 0;
+  for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cin ? cmax : jobs.job[i].cin;
+  dim3 grid((cmax + 7) / 8, jobs.n);
+  style_kernel<<<grid, 256, 0, st>>>(jobs, latent, latent_stride, batch);
+  count_launch();
+  return check_launch("style_kernel") ? 0 : 1;
+}
+
+int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st) {
+  int cmax = 0;
+  for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cout ? cmax : jobs.job[i].cout;
+  dim3 grid((cmax + 7) / 8, batch, jobs.n);
+  table_kernel<<<grid, 256, 0, st>>>(jobs, batch);
+  count_launch();
+  return check_launch("table_kernel") ? 0 : 1;
+}
+
+int demod_launch(const float* s, const float* wsq, int batch, int cin, int cout, float* d, cudaStream_t st) {
+  dim3 grid((cout + 7) / 8, batch);
+  demod_kernel<<<grid, 256, 0, st>>>(s, wsq, cin, cout, d);
+  count_launch();
+  return check_launch("demod_kernel") ? 0 : 1;
+}
+
+int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d,
+                      cudaStream_t st) {
+  const long long total = static_cast<long long>(batch) * (C / 8) * H * W;
+  nchw_to_c8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, scale, batch, C, H, W, s2d,
+                                                                                static_cast<__nv_bfloat16*>(out));
+  count_launch();
+  return check_launch("nchw_to_c8_kernel") ? 0 : 1;
+}
+
+int const_input_launch(const float* cinput, const float* s, int batch, int C, void* out, cudaStream_t st) {
+  const int total = batch * (C / 8) * 16;
+  const_input_kernel<<<(total + 127) / 128, 128, 0, st>>>(cinput, s, batch, C, static_cast<__nv_bfloat16*>(out));
+  count_launch();
+  return check_launch("const_input_kernel") ? 0 : 1;
+}
+
+}  // namespace sgr

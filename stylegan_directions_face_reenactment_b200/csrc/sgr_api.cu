@@ -1,0 +1,316 @@
+// extern "C" surface of libsgr.so (include/sgr.h) and the whole-network orchestration.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sgr_internal.h"
+
+namespace sgr {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { ++g_launches; }
+bool check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+static bool have_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libsgr has no CPU fallback");
+    return false;
+  }
+  return true;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Workspace carve-up for the whole network (all offsets 256-byte aligned).
+struct SynthPlan {
+  size_t style_off[SGR_MAX_STYLED], rgbstyle_off[SGR_MAX_RGB];
+  size_t demod_off[SGR_MAX_STYLED], s2_off[SGR_MAX_STYLED], coef_off[SGR_MAX_STYLED];
+  size_t rgbacc_off[SGR_MAX_RGB];
+  size_t rgbacc_begin, rgbacc_end;
+  size_t skip_off[2];
+  size_t act_off[2];
+  size_t total;
+};
+
+static int plan_synthesis(const sgr_synthesis* net, int batch, SynthPlan* pl) {
+  if (!net || batch <= 0) {
+    set_error("synthesis: null network or batch <= 0");
+    return 1;
+  }
+  if (net->n_styled < 1 || net->n_styled > SGR_MAX_STYLED || net->n_rgb < 1 || net->n_rgb > SGR_MAX_RGB ||
+      net->n_styled != 2 * net->n_rgb - 1) {
+    set_error("synthesis: inconsistent layer counts n_styled=%d n_rgb=%d", net->n_styled, net->n_rgb);
+    return 1;
+  }
+  size_t off = 0;
+  const size_t B = static_cast<size_t>(batch);
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    pl->style_off[l] = off; off = align_up(off + B * L.cin * 4, 256);
+    pl->demod_off[l] = off; off = align_up(off + B * L.cout * 4, 256);
+    pl->s2_off[l] = off; off = align_up(off + B * L.cout * 4, 256);
+    pl->coef_off[l] = off; off = align_up(off + B * 3 * L.cout * 4, 256);
+  }
+  for (int r = 0; r < net->n_rgb; ++r) {
+    pl->rgbstyle_off[r] = off; off = align_up(off + B * net->rgb[r].cin * 4, 256);
+  }
+  pl->rgbacc_begin = off;
+  size_t max_act = 0;
+  for (int r = 0; r < net->n_rgb; ++r) {
+    const size_t res = static_cast<size_t>(4) << r;
+    pl->rgbacc_off[r] = off; off = align_up(off + B * 3 * res * res * 4, 256);
+  }
+  pl->rgbacc_end = off;
+  const size_t S = static_cast<size_t>(net->size);
+  for (int i = 0; i < 2; ++i) {
+    pl->skip_off[i] = off; off = align_up(off + B * 3 * S * S * 4, 256);
+  }
+  // activation ping-pong: hi+lo bf16 = 4 bytes per element; the input of layer 0 is [B,cin,4,4]
+  max_act = B * net->styled[0].cin * 16;
+  for (int l = 0; l + 1 < net->n_styled; ++l) {      // the last layer's activation never leaves the chip
+    const size_t res = static_cast<size_t>(4) << ((l + 1) / 2);
+    const size_t e = B * net->styled[l].cout * res * res;
+    if (e > max_act) max_act = e;
+  }
+  for (int i = 0; i < 2; ++i) {
+    pl->act_off[i] = off; off = align_up(off + max_act * 4, 256);
+  }
+  pl->total = off;
+  return 0;
+}
+
+}  // namespace sgr
+
+using namespace sgr;
+
+extern "C" {
+
+const char* sgr_version(void) { return "sgr 0.1 (sm_100a: tcgen05/TMEM/TMA modconv, bf16x3)"; }
+const char* sgr_last_error(void) { return g_err; }
+long long sgr_launch_count(void) { return g_launches; }
+void sgr_reset_launch_count(void) { g_launches = 0; }
+
+int sgr_upfirdn2d(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int up, int down,
+                  int pad0, int pad1, int kh, int kw, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !y || !taps) {
+    set_error("upfirdn2d: null pointer");
+    return 1;
+  }
+  return upfirdn2d_launch(x, y, taps, planes, in_h, in_w, up, down, pad0, pad1, kh, kw,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
+                       long long inner, int grad, float slope, float scale, void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !y) {
+    set_error("fused_bias_act: null pointer");
+    return 1;
+  }
+  return bias_act_launch(x, bias, ref, y, outer, channels, inner, grad, slope, scale, static_cast<cudaStream_t>(stream));
+}
+
+size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose) {
+  const size_t n_total = transpose ? cin : static_cast<size_t>(cout) * (up ? 4 : 1);
+  const size_t k_total = transpose ? static_cast<size_t>(cout) * (up ? 4 : 1) : cin;
+  return n_total * k_total * ksize * ksize * 2 /*planes*/ * 2 /*bf16*/;
+}
+
+int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up, int transpose,
+                            void* packed, float* wsq, void* stream) {
+  if (!have_device()) return 1;
+  const int n_total = transpose ? cin : cout * (up ? 4 : 1);
+  const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
+  if (!weight || !packed || (up && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
+      k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0) {
+    set_error("pack_modconv_weight: unsupported cout=%d cin=%d k=%d up=%d transpose=%d", cout, cin, ksize, up,
+              transpose);
+    return 1;
+  }
+  return pack_weight_launch(weight, fir, cout, cin, ksize, up, transpose, packed, wsq, static_cast<cudaStream_t>(stream));
+}
+
+int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, int channels, int h, int w, int s2d,
+                   void* stream) {
+  if (!have_device()) return 1;
+  if (!x || !out_c8 || channels % 8 != 0 || (s2d && ((h | w) & 1))) {
+    set_error("nchw_to_c8: bad arguments (C=%d H=%d W=%d)", channels, h, w);
+    return 1;
+  }
+  return nchw_to_c8_launch(x, scale, out_c8, batch, channels, h, w, s2d, static_cast<cudaStream_t>(stream));
+}
+
+int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
+  if (!have_device()) return 1;
+  ConvKernelParams p;
+  int nt = 0;
+  if (conv_fill_params(args, &p, &nt)) return 1;
+  CUtensorMap tmap;
+  if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
+  return launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+}
+
+int sgr_style_affine(const float* latent, int latent_stride, int batch, const float* mod_weight, const float* mod_bias,
+                     int cin, float* s_out, void* stream) {
+  if (!have_device()) return 1;
+  StyleJobs jobs;
+  jobs.n = 1;
+  jobs.job[0] = StyleJob{mod_weight, mod_bias, s_out, cin, 0};
+  return style_jobs_launch(jobs, latent, latent_stride, batch, static_cast<cudaStream_t>(stream));
+}
+
+int sgr_demod(const float* s, const float* wsq, int batch, int cin, int cout, float* d_out, void* stream) {
+  if (!have_device()) return 1;
+  return demod_launch(s, wsq, batch, cin, cout, d_out, static_cast<cudaStream_t>(stream));
+}
+
+size_t sgr_synthesis_workspace_bytes(const sgr_synthesis* net, int batch) {
+  SynthPlan pl;
+  if (plan_synthesis(net, batch, &pl)) return 0;
+  return pl.total;
+}
+
+int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
+                          size_t workspace_bytes, float* const* feats, void* stream) {
+  if (!have_device()) return 1;
+  SynthPlan pl;
+  if (plan_synthesis(net, batch, &pl)) return 1;
+  if (!latent || !image || !workspace || workspace_bytes < pl.total) {
+    set_error("synthesis_forward: workspace too small (%zu < %zu) or null pointer", workspace_bytes, pl.total);
+    return 1;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("synthesis_forward: workspace must be 256-byte aligned");
+    return 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int latent_stride = net->n_latent * SGR_STYLE_DIM;
+
+  // 1. every layer's style vector in one launch
+  StyleJobs sj;
+  sj.n = 0;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    sj.job[sj.n++] = StyleJob{L.mod_weight, L.mod_bias, F(pl.style_off[l]), L.cin, L.latent_row};
+  }
+  for (int r = 0; r < net->n_rgb; ++r) {
+    const sgr_rgb_layer& R = net->rgb[r];
+    sj.job[sj.n++] = StyleJob{R.mod_weight, R.mod_bias, F(pl.rgbstyle_off[r]), R.cin, R.latent_row};
+  }
+  if (style_jobs_launch(sj, latent, latent_stride, batch, st)) return 1;
+
+  // 2. demodulation + epilogue tables (next layer's style, fused ToRGB coefficients)
+  TableJobs tj;
+  tj.n = net->n_styled;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    TableJob& j = tj.job[l];
+    j.s = F(pl.style_off[l]);
+    j.wsq = L.wsq;
+    j.demod = F(pl.demod_off[l]);
+    j.cin = L.cin;
+    j.cout = L.cout;
+    const bool has_next = l + 1 < net->n_styled;
+    j.s_next = has_next ? F(pl.style_off[l + 1]) : nullptr;
+    j.s2 = F(pl.s2_off[l]);
+    const bool has_rgb = !L.up;                 // conv1 and every odd convs.* feed a ToRGB
+    const int r = (l + 1) / 2;
+    j.s_rgb = has_rgb ? F(pl.rgbstyle_off[r]) : nullptr;
+    j.w_rgb = has_rgb ? net->rgb[r].weight : nullptr;
+    j.rgb_coef = F(pl.coef_off[l]);
+    if (has_next && net->styled[l + 1].cin != L.cout) {
+      set_error("synthesis_forward: layer %d cout %d != layer %d cin %d", l, L.cout, l + 1, net->styled[l + 1].cin);
+      return 1;
+    }
+    if (has_rgb && net->rgb[r].cin != L.cout) {
+      set_error("synthesis_forward: rgb %d cin mismatch", r);
+      return 1;
+    }
+  }
+  if (table_jobs_launch(tj, batch, st)) return 1;
+
+  // 3. zero the fused-ToRGB accumulators; modulated constant input
+  if (cudaMemsetAsync(ws + pl.rgbacc_begin, 0, pl.rgbacc_end - pl.rgbacc_begin, st) != cudaSuccess) {
+    set_error("synthesis_forward: memset failed");
+    return 1;
+  }
+  int cur = 0;
+  if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, net->styled[0].cin, ws + pl.act_off[cur], st))
+    return 1;
+
+  // 4. the layer chain
+  int res = 4;
+  int skip_cur = 0;
+  const float* prev_skip = nullptr;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    const bool last = l + 1 == net->n_styled;
+    sgr_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch;
+    a.cin = L.cin;
+    a.cout = L.cout;
+    a.h_in = res;
+    a.w_in = res;
+    a.ksize = 3;
+    a.up = L.up;
+    a.act = 1;
+    a.act_gain = 1.4142135623730951f;
+    a.x_c8 = ws + pl.act_off[cur];
+    a.w_packed = L.w_packed;
+    a.demod = F(pl.demod_off[l]);
+    a.bias = L.act_bias;
+    a.noise = L.noise;
+    a.noise_batch_stride = L.noise_batch_stride;
+    a.noise_weight = L.noise_weight;
+    a.s2 = last ? nullptr : F(pl.s2_off[l]);
+    a.out_c8 = last ? nullptr : ws + pl.act_off[1 - cur];
+    a.out_f32 = feats ? feats[l] : nullptr;
+    const int r = (l + 1) / 2;
+    if (!L.up) {
+      a.rgb_coef = F(pl.coef_off[l]);
+      a.rgb_acc = F(pl.rgbacc_off[r]);
+    }
+    if (sgr_modconv_forward(&a, stream)) return 1;
+    if (L.up) res *= 2;
+    cur = 1 - cur;
+    if (!L.up) {
+      const sgr_rgb_layer& R = net->rgb[r];
+      float* dst = last ? image : F(pl.skip_off[skip_cur]);
+      if (prev_skip && !R.fir) {
+        set_error("synthesis_forward: rgb %d needs an upsample kernel", r);
+        return 1;
+      }
+      if (torgb_tail_launch(F(pl.rgbacc_off[r]), R.bias, prev_skip, R.fir, dst, batch, res, res, st)) return 1;
+      prev_skip = dst;
+      skip_cur = 1 - skip_cur;
+    }
+  }
+  if (res != net->size) {
+    set_error("synthesis_forward: layer chain ends at %d, expected %d", res, net->size);
+    return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

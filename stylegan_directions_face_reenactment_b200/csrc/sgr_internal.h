@@ -1,0 +1,99 @@
+// Internal declarations shared by the .cu files of libsgr.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/sgr.h"
+
+namespace sgr {
+
+constexpr int kTileM = 128;      // GEMM rows (pixels) per CTA tile == TMEM lanes
+constexpr int kBlockK = 32;      // input channels per pipeline stage (4 chunks of 8)
+constexpr int kABytes = 2 * kTileM * kBlockK * 2;   // hi+lo planes of one A stage = 16 KiB
+
+// GEMM column tile for a layer with n_total columns.
+inline int pick_nt(int n_total) { return n_total >= 256 ? 256 : n_total; }
+
+void set_error(const char* fmt, ...);
+void count_launch();
+bool check_launch(const char* what);
+
+struct ConvKernelParams {
+  int B, H, W;                  // pixel space of the implicit GEMM (input resolution)
+  int bw, bh, bb;               // tile box (bw*bh*bb == 128)
+  int tiles_x, tiles_y, tiles_b;
+  int m_tiles, n_tiles;
+  int kchunks;                  // cin / 32
+  int ntaps;                    // 9 or 1
+  int cout;                     // real output channels (power of two)
+  int up;
+  int Hout, Wout;
+  int act;
+  float act_gain;
+  const __nv_bfloat16* wpacked;
+  const float* demod;
+  const float* bias;
+  const float* noise;
+  const float* noise_w;
+  long long noise_bstride;       // 0: one noise map shared by the batch
+  const float* s2;
+  __nv_bfloat16* out_c8;
+  float* out_f32;
+  const float* rgb_coef;
+  float* rgb_acc;
+};
+
+// modconv_sm100.cu
+int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
+// host: build the 5-D tensor map over C8 activation planes
+int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
+                        int bb);
+int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
+
+// prep_kernels.cu
+struct StyleJob {
+  const float* mod_weight;   // [cin, 512]
+  const float* mod_bias;     // [cin]
+  float* out;                // [B, cin]
+  int cin;
+  int latent_row;
+};
+struct StyleJobs {
+  StyleJob job[SGR_MAX_STYLED + SGR_MAX_RGB];
+  int n;
+};
+struct TableJob {
+  const float* s;        // [B, cin]   this layer's style
+  const float* wsq;      // [cout, cin]
+  float* demod;          // [B, cout]
+  const float* s_next;   // [B, cout]  next conv's style or NULL
+  float* s2;             // [B, cout]  sqrt2 * s_next
+  const float* s_rgb;    // [B, cout]  following ToRGB's style or NULL
+  const float* w_rgb;    // [3, cout]
+  float* rgb_coef;       // [B, 3, cout]
+  int cin, cout;
+};
+struct TableJobs {
+  TableJob job[SGR_MAX_STYLED];
+  int n;
+};
+int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose,
+                       void* packed, float* wsq, cudaStream_t st);
+int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st);
+int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st);
+int demod_launch(const float* s, const float* wsq, int batch, int cin, int cout, float* d, cudaStream_t st);
+int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d,
+                      cudaStream_t st);
+int const_input_launch(const float* cinput, const float* s, int batch, int C, void* out, cudaStream_t st);
+// upfirdn2d_sm100.cu
+int upfirdn2d_launch(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int up, int down,
+                     int pad0, int pad1, int kh, int kw, cudaStream_t st);
+int bias_act_launch(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
+                    long long inner, int grad, float slope, float scale, cudaStream_t st);
+int torgb_tail_launch(const float* rgb_acc, const float* bias, const float* skip_in, const float* fir, float* out,
+                      int batch, int H, int W, cudaStream_t st);
+
+}  // namespace sgr

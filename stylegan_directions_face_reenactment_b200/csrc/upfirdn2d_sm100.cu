@@ -1,0 +1,271 @@
+// HBM-bound kernels: upfirdn2d (replaces op/upfirdn2d_kernel.cu:52-272), fused bias + leaky-relu
+// (replaces op/fused_bias_act_kernel.cu:18-99) and the ToRGB tail (bias + 2x FIR-upsampled skip, model.py:355-359).
+#include "sgr_internal.h"
+
+namespace sgr {
+
+// ------------------------------------------------------------------------------------------------ upfirdn2d
+// y[p, oy, ox] = sum_{ky,kx} taps[kh-1-ky][kw-1-kx] * u[oy*down + ky - pad0][ox*down + kx - pad0]
+// where u is x zero-inserted by `up` (u[i*up][j*up] = x[i][j]) and zero outside (upfirdn2d_kernel.cu:77,100,125-129).
+//
+// Vectorised over x: each thread produces VX adjacent outputs of one row; a warp covers 32*VX contiguous outputs, so
+// loads and stores are fully coalesced.  For up == down == 1 the horizontal window of a thread overlaps its lane
+// neighbour's: each lane loads only its own VX-aligned span (+ the right-most lane the halo) and the KW-1 halo values
+// come from the next lane through warp shuffles, so every input element is read from L1/L2 once per row pass.
+template <int UP, int DOWN, int KH, int KW, int VX>
+__global__ void upfirdn2d_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ taps,
+                                 int planes, int in_h, int in_w, int out_h, int out_w, int pad0) {
+  __shared__ float sk[KH * KW];
+  if (threadIdx.x < KH * KW) sk[threadIdx.x] = taps[(KH - 1 - threadIdx.x / KW) * KW + (KW - 1 - threadIdx.x % KW)];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * VX;
+  const int oy = blockIdx.y;
+  const bool col_ok = ox0 < out_w;
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const float* xp = x + static_cast<size_t>(pl) * in_h * in_w;
+    float acc[VX];
+#pragma unroll
+    for (int v = 0; v < VX; ++v) acc[v] = 0.f;
+    if (UP == 1 && DOWN == 1) {
+      // window columns ox0 - pad0 .. ox0 - pad0 + VX + KW - 2
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        const int iy = oy + ky - pad0;
+        const bool row_ok = iy >= 0 && iy < in_h;          // warp-uniform
+        float own[VX];
+#pragma unroll
+        for (int v = 0; v < VX; ++v) {
+          const int ix = ox0 + v - pad0;
+          own[v] = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
+        }
+        float win[VX + KW - 1];
+#pragma unroll
+        for (int v = 0; v < VX; ++v) win[v] = own[v];
+#pragma unroll
+        for (int h = 0; h < KW - 1; ++h) {
+          // halo value h = neighbour lane's own[h]; the last lane of the warp loads it directly
+          float nb = __shfl_down_sync(0xffffffffu, own[h % VX], 1 + h / VX);
+          if (lane + 1 + h / VX > 31) {
+            const int ix = ox0 + VX + h - pad0;
+            nb = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
+          }
+          win[VX + h] = nb;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+          const float t = sk[ky * KW + kx];
+#pragma unroll
+          for (int v = 0; v < VX; ++v) acc[v] = fmaf(t, win[v + kx], acc[v]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        const int uy = oy * DOWN + ky - pad0;
+        if (uy < 0 || uy % UP != 0) continue;
+        const int iy = uy / UP;
+        if (iy >= in_h) continue;
+#pragma unroll
+        for (int v = 0; v < VX; ++v) {
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) {
+            const int ux = (ox0 + v) * DOWN + kx - pad0;
+            if (ux < 0 || ux % UP != 0) continue;
+            const int ix = ux / UP;
+            if (ix >= in_w) continue;
+            acc[v] = fmaf(sk[ky * KW + kx], __ldg(xp + static_cast<size_t>(iy) * in_w + ix), acc[v]);
+          }
+        }
+      }
+    }
+    if (col_ok) {
+      float* yp = y + (static_cast<size_t>(pl) * out_h + oy) * out_w + ox0;
+      if (VX == 4 && (out_w % 4) == 0) {
+        *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VX; ++v)
+          if (ox0 + v < out_w) yp[v] = acc[v];
+      }
+    }
+  }
+}
+
+// Any factors / tap counts (correctness path for shapes outside the generator's four modes).
+__global__ void upfirdn2d_generic_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                         const float* __restrict__ taps, int planes, int in_h, int in_w, int out_h,
+                                         int out_w, int up, int down, int pad0, int kh, int kw) {
+  const long long total = static_cast<long long>(planes) * out_h * out_w;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % out_w);
+    const int oy = static_cast<int>((idx / out_w) % out_h);
+    const long long pl = idx / (static_cast<long long>(out_w) * out_h);
+    const float* xp = x + pl * in_h * in_w;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int uy = oy * down + ky - pad0;
+      if (uy < 0 || uy % up != 0 || uy / up >= in_h) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ux = ox * down + kx - pad0;
+        if (ux < 0 || ux % up != 0 || ux / up >= in_w) continue;
+        acc = fmaf(__ldg(taps + (kh - 1 - ky) * kw + (kw - 1 - kx)), __ldg(xp + static_cast<size_t>(uy / up) * in_w + ux / up), acc);
+      }
+    }
+    y[idx] = acc;
+  }
+}
+
+template <int UP, int DOWN>
+static void launch_ufd44(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int out_h,
+                         int out_w, int pad0, cudaStream_t st) {
+  constexpr int VX = 4;
+  const int threads = out_w >= 512 ? 128 : (out_w >= 256 ? 64 : 32);
+  dim3 grid((out_w + threads * VX - 1) / (threads * VX), out_h, planes < 65535 ? planes : 65535);
+  upfirdn2d_kernel<UP, DOWN, 4, 4, VX><<<grid, threads, 0, st>>>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0);
+}
+
+int upfirdn2d_launch(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int up, int down,
+                     int pad0, int pad1, int kh, int kw, cudaStream_t st) {
+  const int out_h = (in_h * up + pad0 + pad1 - kh + down) / down;
+  const int out_w = (in_w * up + pad0 + pad1 - kw + down) / down;
+  if (planes <= 0 || out_h <= 0 || out_w <= 0 || up < 1 || down < 1 || kh < 1 || kw < 1) {
+    set_error("upfirdn2d: empty or invalid shape (planes=%d out=%dx%d up=%d down=%d k=%dx%d)", planes, out_h, out_w,
+              up, down, kh, kw);
+    return 1;
+  }
+  if (kh == 4 && kw == 4 && out_h <= 65535 && up == 1 && down == 1) {
+    launch_ufd44<1, 1>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
+  } else if (kh == 4 && kw == 4 && out_h <= 65535 && up == 2 && down == 1) {
+    launch_ufd44<2, 1>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
+  } else if (kh == 4 && kw == 4 && out_h <= 65535 && up == 1 && down == 2) {
+    launch_ufd44<1, 2>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
+  } else {
+    const long long total = static_cast<long long>(planes) * out_h * out_w;
+    const long long blocks = (total + 255) / 256;
+    upfirdn2d_generic_kernel<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(
+        x, y, taps, planes, in_h, in_w, out_h, out_w, up, down, pad0, kh, kw);
+  }
+  count_launch();
+  return check_launch("upfirdn2d_kernel") ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------ fused bias act
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                const float* __restrict__ ref, float* __restrict__ y, long long total, int channels,
+                                long long inner, int grad, float slope, float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = __ldg(x + i);
+    if (grad == 0) {
+      if (bias) v += __ldg(bias + (i / inner) % channels);
+      y[i] = (v > 0.f ? v : v * slope) * scale;
+    } else {
+      y[i] = (__ldg(ref + i) > 0.f ? v : v * slope) * scale;
+    }
+  }
+}
+
+__global__ void bias_act_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ bias,
+                                     const float4* __restrict__ ref, float4* __restrict__ y, long long total4,
+                                     int channels, long long inner, int grad, float slope, float scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (grad == 0) {
+      const float b = bias ? __ldg(bias + ((i * 4) / inner) % channels) : 0.f;   // inner % 4 == 0: one channel per vec
+      v.x += b; v.y += b; v.z += b; v.w += b;
+      v.x = (v.x > 0.f ? v.x : v.x * slope) * scale;
+      v.y = (v.y > 0.f ? v.y : v.y * slope) * scale;
+      v.z = (v.z > 0.f ? v.z : v.z * slope) * scale;
+      v.w = (v.w > 0.f ? v.w : v.w * slope) * scale;
+    } else {
+      const float4 r = __ldg(ref + i);
+      v.x = (r.x > 0.f ? v.x : v.x * slope) * scale;
+      v.y = (r.y > 0.f ? v.y : v.y * slope) * scale;
+      v.z = (r.z > 0.f ? v.z : v.z * slope) * scale;
+      v.w = (r.w > 0.f ? v.w : v.w * slope) * scale;
+    }
+    y[i] = v;
+  }
+}
+
+int bias_act_launch(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
+                    long long inner, int grad, float slope, float scale, cudaStream_t st) {
+  const long long total = outer * channels * inner;
+  if (total <= 0) return 0;
+  if (grad != 0 && !ref) {
+    set_error("fused_bias_act: grad=1 needs the saved output");
+    return 1;
+  }
+  const bool vec = (inner % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                                         reinterpret_cast<uintptr_t>(ref)) % 16 == 0);
+  if (vec) {
+    const long long t4 = total / 4;
+    const long long blocks = (t4 + 255) / 256;
+    bias_act_vec4_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(x), bias, reinterpret_cast<const float4*>(ref), reinterpret_cast<float4*>(y), t4,
+        channels, inner, grad, slope, scale);
+  } else {
+    const long long blocks = (total + 255) / 256;
+    bias_act_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+        x, bias, ref, y, total, channels, inner, grad, slope, scale);
+  }
+  count_launch();
+  return check_launch("bias_act_kernel") ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------------ ToRGB tail
+// skip_out[b,c,y,x] = rgb_acc[b,c,y,x] + bias[c] + upfirdn2d(skip_in, fir, up=2, pad=(2,1))[b,c,y,x]   (model.py:355-359)
+// skip_in is [B,3,H/2,W/2] (or NULL for to_rgb1).  4 outputs per thread along x.
+__global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, const float* __restrict__ bias,
+                                  const float* __restrict__ skip_in, const float* __restrict__ fir,
+                                  float* __restrict__ out, int planes, int H, int W) {
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = fir ? fir[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)] : 0.f;
+  __syncthreads();
+  const long long total4 = static_cast<long long>(planes) * H * (W / 4);
+  const int h2 = H / 2, w2 = W / 2;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total4;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x0 = static_cast<int>(idx % (W / 4)) * 4;
+    const int y = static_cast<int>((idx / (W / 4)) % H);
+    const int pl = static_cast<int>(idx / (static_cast<long long>(W / 4) * H));
+    const float b = __ldg(bias + pl % 3);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rgb_acc + (static_cast<size_t>(pl) * H + y) * W + x0));
+    float acc[4] = {a.x + b, a.y + b, a.z + b, a.w + b};
+    if (skip_in) {
+      const float* sp = skip_in + static_cast<size_t>(pl) * h2 * w2;
+      // u[j] = skip[j/2] for even j; out[y] = sum_k flipped_taps[k] * u[y + k - 2]
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int uy = y + ky - 2;
+        if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+        const float* row = sp + static_cast<size_t>(uy >> 1) * w2;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) {
+            const int ux = x0 + v + kx - 2;
+            if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+            acc[v] = fmaf(sk[ky * 4 + kx], __ldg(row + (ux >> 1)), acc[v]);
+          }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(out + (static_cast<size_t>(pl) * H + y) * W + x0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+int torgb_tail_launch(const float* rgb_acc, const float* bias, const float* skip_in, const float* fir, float* out,
+                      int batch, int H, int W, cudaStream_t st) {
+  const long long total4 = static_cast<long long>(batch) * 3 * H * (W / 4);
+  const long long blocks = (total4 + 255) / 256;
+  torgb_tail_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+      rgb_acc, bias, skip_in, fir, out, batch * 3, H, W);
+  count_launch();
+  return check_launch("torgb_tail_kernel") ? 0 : 1;
+}
+
+}  // namespace sgr

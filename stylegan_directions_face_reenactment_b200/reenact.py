@@ -1,0 +1,37 @@
+"""Glue between the direction matrix and the generator (reference libs/utilities/generic.py:116-152)."""
+import torch
+
+
+def get_shifted_latent_code(G, z, shift, input_is_latent=False, truncation=1, truncation_latent=None, w_plus=True,
+                            num_layers=None):
+    """latent = z.clone(); latent[:, :num_layers] += shift  (generic.py:116-135).  The caller's z is never mutated."""
+    n_latent = G.n_latent
+    if not input_is_latent:
+        w = G.get_latent(z)
+        latent = w.unsqueeze(1).repeat(1, n_latent, 1)
+    else:
+        latent = z.clone()
+    if w_plus:                       # shift [B, k, 512] goes into the first k rows (generic.py:132-133)
+        k = shift.shape[1]
+        latent = torch.cat([latent[:, :k, :] + shift, latent[:, k:, :]], 1)
+    else:                            # shift [B, 512]: every row, or the first num_layers rows (generic.py:123-130)
+        k = n_latent if num_layers is None else num_layers
+        latent = torch.cat([latent[:, :k, :] + shift.unsqueeze(1), latent[:, k:, :]], 1)
+    return latent
+
+
+def generate_image(G, latent_code, truncation, trunc, w_plus=True, num_layers_shift=8, shift_code=None,
+                   input_is_latent=False, return_latents=False):
+    """generic.py:137-152: optional shift, then G([code], truncation, ...), 256-pooling for larger nets."""
+    if shift_code is None:
+        imgs, latents = G([latent_code], return_latents=return_latents, truncation=truncation,
+                          truncation_latent=trunc, input_is_latent=input_is_latent)
+    else:
+        shifted = get_shifted_latent_code(G, latent_code, shift_code, input_is_latent=input_is_latent,
+                                          truncation=truncation, truncation_latent=trunc, w_plus=w_plus,
+                                          num_layers=num_layers_shift)
+        imgs, latents = G([shifted], return_latents=return_latents, truncation=truncation, truncation_latent=trunc,
+                          input_is_latent=True)
+    if imgs.shape[2] > 256:
+        imgs = torch.nn.functional.adaptive_avg_pool2d(imgs, (256, 256))
+    return (imgs, latents) if return_latents else imgs

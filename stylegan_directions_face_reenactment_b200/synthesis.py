@@ -1,0 +1,127 @@
+"""Whole-network execution: fills the C `sgr_synthesis` descriptor from a Generator's parameters and calls
+sgr_synthesis_forward (one C call = all kernel launches of Generator.forward's synthesis part, reference
+model.py:519-534)."""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+class NetDescriptor:
+    """Keeps the ctypes struct and every tensor it points to alive for the duration of a call."""
+
+    def __init__(self, g, noise, batch):
+        self.keep = []
+        s = N.Synthesis()
+        styled = g.styled_layers()
+        rgbs = g.rgb_layers()
+        s.size, s.n_styled, s.n_rgb, s.n_latent = g.size, len(styled), len(rgbs), g.n_latent
+        s.const_input = self._p(g.input.input)
+        for l, layer in enumerate(styled):
+            conv = layer.conv
+            packed, wsq = conv.packed()
+            d = s.styled[l]
+            d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, int(conv.upsample)
+            d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
+            d.w_packed, d.wsq = self._p(packed), self._p(wsq)
+            d.mod_weight, d.mod_bias = self._p(conv.modulation.weight), self._p(conv.modulation.bias)
+            nz = noise[l]
+            res = 4 << ((l + 1) // 2)
+            if nz is None:                             # randomize_noise: fresh per-sample noise (model.py:282-285)
+                nz = torch.randn(batch, 1, res, res, device=g.input.input.device)
+            if nz.shape[-1] != res or nz.shape[-2] != res:
+                raise RuntimeError('noise %d has shape %s, expected [*,1,%d,%d]' % (l, tuple(nz.shape), res, res))
+            d.noise = self._p(nz)
+            d.noise_batch_stride = res * res if (nz.shape[0] == batch and batch > 1) else 0
+            d.noise_weight = self._p(layer.noise.weight)
+            d.act_bias = self._p(layer.activate.bias)
+        for r, layer in enumerate(rgbs):
+            d = s.rgb[r]
+            d.cin = layer.conv.in_channel
+            d.latent_row = 1 if r == 0 else 2 * r + 1  # to_rgb1 <- row 1, to_rgbs[b] <- row 2b+3
+            d.weight = self._p(layer.conv.weight)
+            d.mod_weight, d.mod_bias = self._p(layer.conv.modulation.weight), self._p(layer.conv.modulation.bias)
+            d.bias = self._p(layer.bias)
+            d.fir = self._p(layer.upsample.kernel) if hasattr(layer, 'upsample') else None
+        self.struct = s
+
+    def _p(self, t):
+        t = _f32c(t) if t.dtype != torch.uint8 else t
+        self.keep.append(t)
+        return N.ptr(t)
+
+
+def _workspace(g, desc, batch, device):
+    key = (batch, device.index)
+    ws = g._workspace.get(key)
+    if ws is None:
+        nbytes = N.lib().sgr_synthesis_workspace_bytes(C.byref(desc.struct), batch)
+        if nbytes == 0:
+            raise RuntimeError('sgr_synthesis_workspace_bytes: %s' % N.lib().sgr_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        g._workspace.clear()                           # one live workspace per generator
+        g._workspace[key] = ws
+    return ws
+
+
+def synthesis_forward(g, latent, noise, want_feats):
+    if not latent.is_cuda:
+        raise RuntimeError('Generator: latent must be a CUDA tensor (libsgr has no CPU fallback)')
+    if latent.ndim != 3 or latent.shape[1] != g.n_latent or latent.shape[2] != g.style_dim:
+        raise RuntimeError('latent must be [B,%d,%d], got %s' % (g.n_latent, g.style_dim, tuple(latent.shape)))
+    lat = _f32c(latent)
+    batch = lat.shape[0]
+    dev = lat.device
+    with torch.cuda.device(dev):
+        desc = NetDescriptor(g, noise, batch)
+        ws = _workspace(g, desc, batch, dev)
+        image = torch.empty(batch, 3, g.size, g.size, device=dev, dtype=torch.float32)
+        feats, feat_ptrs = None, None
+        if want_feats:
+            feats = []
+            arr = (C.c_void_p * len(g.styled_layers()))()
+            for l, layer in enumerate(g.styled_layers()):
+                res = 4 << ((l + 1) // 2)
+                f = torch.empty(batch, layer.conv.out_channel, res, res, device=dev, dtype=torch.float32)
+                feats.append(f)
+                arr[l] = f.data_ptr()
+            feat_ptrs = arr
+        N.check(N.lib().sgr_synthesis_forward(C.byref(desc.struct), N.ptr(lat), batch, N.ptr(image), N.ptr(ws),
+                                              ws.numel(), feat_ptrs, N.stream()), 'sgr_synthesis_forward')
+    return image, feats, lat
+
+
+class _Synthesis(torch.autograd.Function):
+    """Autograd node for dL/d(latent) — the only gradient the A-matrix training consumes (libs/trainer.py:144,187-189)."""
+
+    @staticmethod
+    def forward(ctx, latent, g, noise):
+        image, feats, lat = synthesis_forward(g, latent, noise, want_feats=True)
+        ctx.g = g
+        ctx.noise = noise
+        ctx.save_for_backward(lat, *feats)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        from .backward import synthesis_backward
+        lat, *feats = ctx.saved_tensors
+        return synthesis_backward(ctx.g, lat, feats, ctx.noise, grad_image), None, None
+
+
+def run_synthesis(g, latent, noise, return_features=False):
+    if return_features:
+        image, feats, _ = synthesis_forward(g, latent, noise, want_feats=True)
+        return image, feats
+    if torch.is_grad_enabled() and latent.requires_grad:
+        return _Synthesis.apply(latent, g, noise)
+    image, _, _ = synthesis_forward(g, latent, noise, want_feats=False)
+    return image

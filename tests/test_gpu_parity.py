@@ -1,0 +1,251 @@
+"""GPU parity: libsgr.so (through the C ABI) against the committed reference goldens and the CPU oracle.
+
+Tolerances (fp32 path computed as bf16x3 split products with fp32 accumulation; north_star bar: pixel max-abs <= 1e-3):
+  upfirdn2d / bias-act (pure fp32)             2e-6 .. 1e-5 abs
+  one modulated conv, outputs O(1)             1e-4 abs
+  full generator image (random init, +-9)      1e-3 abs
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stylegan2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import stylegan_directions_face_reenactment_b200 as p
+    from stylegan_directions_face_reenactment_b200 import _native
+    _native.lib()          # fail loudly if libsgr.so is missing
+    return p
+
+
+def err(a, b):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else a
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.abs(a - b).max())
+
+
+def cuda(x):
+    return T(x).cuda()
+
+
+# ------------------------------------------------------------------------------------------ native ops
+def test_upfirdn2d_golden(pkg, golden):
+    g = golden('upfirdn2d.npz')
+    tags = sorted(k[:-4] for k in g if k.endswith('_cfg'))
+    assert len(tags) == 9
+    for t in tags:
+        up, down, p0, p1 = [int(v) for v in g[t + '_cfg']]
+        y = pkg.upfirdn2d(cuda(g[t + '_x']), cuda(g[t + '_k']), up=up, down=down, pad=(p0, p1))
+        assert err(y, g[t + '_y']) <= 2e-6, t
+
+
+def test_upfirdn2d_generator_modes_vs_oracle(pkg):
+    rng = np.random.Generator(np.random.PCG64(5))
+    fir = orc.make_fir_kernel([1, 3, 3, 1]) * 4
+    for shape, up, down, pad in [((3, 7, 65, 65), 1, 1, (1, 1)), ((2, 3, 128, 128), 2, 1, (2, 1)),
+                                 ((2, 3, 256, 256), 1, 2, (1, 1)), ((1, 2, 513, 513), 1, 1, (1, 1)),
+                                 ((1, 1, 9, 1031), 1, 1, (2, 2))]:
+        x = T(rng.standard_normal(shape, dtype=np.float32))
+        ref = orc.upfirdn2d(x, fir, up, down, pad).numpy()
+        y = pkg.upfirdn2d(x.cuda(), fir.cuda(), up=up, down=down, pad=pad)
+        assert err(y, ref) <= 5e-6, (shape, up, down)
+
+
+def test_upfirdn2d_backward_matches_oracle_autograd(pkg):
+    rng = np.random.Generator(np.random.PCG64(6))
+    fir = orc.make_fir_kernel([1, 3, 3, 1]) * 4
+    for shape, up, down, pad in [((2, 3, 9, 9), 1, 1, (1, 1)), ((2, 3, 8, 8), 2, 1, (2, 1)), ((1, 2, 16, 16), 1, 2, (1, 1))]:
+        x = T(rng.standard_normal(shape, dtype=np.float32))
+        xr = x.clone().requires_grad_(True)
+        yr = orc.upfirdn2d(xr, fir, up, down, pad)
+        gy = T(rng.standard_normal(tuple(yr.shape), dtype=np.float32))
+        yr.backward(gy)
+        xg = x.cuda().requires_grad_(True)
+        y = pkg.upfirdn2d(xg, fir.cuda(), up=up, down=down, pad=pad)
+        y.backward(gy.cuda())
+        assert err(xg.grad, xr.grad.numpy()) <= 5e-6
+
+
+def test_bias_act_golden(pkg, golden):
+    g = golden('bias_act.npz')
+    x = cuda(g['x']).requires_grad_(True)
+    b = cuda(g['b']).requires_grad_(True)
+    y = pkg.fused_leaky_relu(x, b)
+    assert err(y, g['y']) <= 1e-6
+    y.backward(cuda(g['g']))
+    assert err(x.grad, g['gx']) <= 1e-6
+    assert err(b.grad, g['gb']) <= 2e-5
+    assert err(pkg.fused_leaky_relu(cuda(g['x2']), cuda(g['b2'])), g['y2']) <= 1e-6
+
+
+def test_ops_reject_cpu_tensors(pkg):
+    with pytest.raises(RuntimeError):
+        pkg.fused_leaky_relu(torch.zeros(2, 4), torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        pkg.upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+    g = pkg.Generator(8, 512, 8)
+    with pytest.raises(RuntimeError):
+        g([torch.zeros(1, g.n_latent, 512)], input_is_latent=True)
+
+
+# ------------------------------------------------------------------------------------------ modulated conv
+def test_modconv_golden(pkg, golden):
+    g = golden('modconv.npz')
+    for tag, demod, up, k in [('plain', True, False, 3), ('up', True, True, 3), ('rgb', False, False, 1),
+                              ('plain64', True, False, 3), ('up64', True, True, 3)]:
+        w = g[tag + '_weight']
+        m = pkg.ModulatedConv2d(w.shape[2], w.shape[1], k, 512, demodulate=demod, upsample=up).cuda()
+        with torch.no_grad():
+            m.weight.copy_(cuda(w))
+            m.modulation.weight.copy_(cuda(g[tag + '_mw']))
+            m.modulation.bias.copy_(cuda(g[tag + '_mb']))
+        y = m(cuda(g[tag + '_x']), cuda(g[tag + '_w']))
+        ref = g[tag + '_y']
+        assert err(y, ref) <= 1e-4 * max(1.0, np.abs(ref).max()), tag
+
+
+def test_styled_block_golden(pkg, golden):
+    """BASELINE config 1: StyledConv(up) -> StyledConv -> ToRGB(+skip), module-level calls, every intermediate."""
+    g = golden('styled_block.npz')
+    sd = {k[2:]: cuda(v) for k, v in g.items() if k.startswith('p.')}
+    c0 = pkg.StyledConv(32, 64, 3, 512, upsample=True).cuda()
+    c1 = pkg.StyledConv(64, 64, 3, 512).cuda()
+    tr = pkg.ToRGB(64, 512).cuda()
+    for pre, mod in [('c0', c0), ('c1', c1), ('rgb', tr)]:
+        mod.load_state_dict({k[len(pre) + 1:]: v for k, v in sd.items() if k.startswith(pre + '.')}, strict=False)
+    y0 = c0(cuda(g['x']), cuda(g['w0']), noise=cuda(g['n0']))
+    y1 = c1(y0, cuda(g['w1']), noise=cuda(g['n1']))
+    rgb = tr(y1, cuda(g['w2']), cuda(g['skip']))
+    assert err(y0, g['y0']) <= 1e-4 * np.abs(g['y0']).max()
+    assert err(y1, g['y1']) <= 1e-4 * np.abs(g['y1']).max()
+    assert err(rgb, g['rgb']) <= 2e-4 * np.abs(g['rgb']).max()
+
+
+# ------------------------------------------------------------------------------------------ generator
+def _gen(pkg, golden, name):
+    g = golden(name)
+    size, cm, seed, batch = [int(v) for v in g['cfg']]
+    sd = orc.seeded_state_dict(size, cm, seed=seed)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    return g, size, cm, sd, G.cuda().eval()
+
+
+@pytest.mark.parametrize('name', ['generator_8_cm2.npz', 'generator_32_cm2.npz'])
+def test_generator_small_golden(pkg, golden, name):
+    g, size, cm, sd, G = _gen(pkg, golden, name)
+    with torch.no_grad():
+        img, feats = G.synthesis(cuda(g['wplus']), return_features=True)
+        st = int(g['feat_stride'])
+        for i, f in enumerate(feats):
+            ref = g['feat%d' % i]
+            assert err(f[:, ::st], ref) <= 2e-4 * max(1.0, np.abs(ref).max()), ('feat', i)
+        assert err(img, g['img']) <= 1e-3
+        img2, none = G([cuda(g['wplus'])], input_is_latent=True)
+        assert none is None and err(img2, g['img']) <= 1e-3
+        img_t, _ = G([cuda(g['wplus'])], input_is_latent=True, truncation=0.7, truncation_latent=cuda(g['trunc']))
+        assert err(img_t, g['img_trunc']) <= 1e-3
+        img_z, lat_z = G([cuda(g['zin'])], return_latents=True, truncation=0.7, truncation_latent=cuda(g['trunc']))
+        assert err(lat_z, g['lat_z']) <= 1e-4
+        assert err(img_z, g['img_z']) <= 1e-3
+
+
+def test_generator_256_golden(pkg, golden):
+    """BASELINE config 2 network (256^2, channel_multiplier=1) against the reference's own output."""
+    g, size, cm, sd, G = _gen(pkg, golden, 'generator_256_cm1.npz')
+    with torch.no_grad():
+        img, feats = G.synthesis(cuda(g['wplus']), return_features=True)
+    e = err(img, g['img'])
+    assert e <= 1e-3, e
+    np.testing.assert_allclose([f.abs().mean().item() for f in feats], g['feat_absmean'], rtol=1e-3)
+
+
+def test_generator_256_batch8_vs_oracle_and_properties(pkg):
+    """Config 2 at full size (B=8): oracle parity on 2 samples + batch-independence + determinism."""
+    size, cm = 256, 1
+    sd = orc.seeded_state_dict(size, cm, seed=0)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, 8, G.n_latent, seed=1234)
+    with torch.no_grad():
+        img = G([wplus.cuda()], input_is_latent=True)[0]
+        img_again = G([wplus.cuda()], input_is_latent=True)[0]
+        assert torch.equal(img, img_again)                                   # deterministic (<= 2 atomics per address)
+        sub = G([wplus[5:7].cuda()], input_is_latent=True)[0]
+        assert err(sub, img[5:7].cpu().numpy()) <= 1e-5                      # samples are independent
+        ref, _ = orc.generator_forward(sd, [wplus[5:7]], size, cm, input_is_latent=True)
+    assert err(img[5:7], ref.numpy()) <= 1e-3
+    assert tuple(img.shape) == (8, 3, 256, 256) and torch.isfinite(img).all()
+
+
+def test_generator_odd_batches_and_noise_modes(pkg):
+    size, cm = 32, 2
+    sd = orc.seeded_state_dict(size, cm, seed=4)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    for b in (1, 3, 5, 9):
+        wplus = orc.seeded_wplus(sd, b, G.n_latent, seed=b)
+        with torch.no_grad():
+            img = G([wplus.cuda()], input_is_latent=True)[0]
+            ref, _ = orc.generator_forward(sd, [wplus], size, cm, input_is_latent=True)
+        assert err(img, ref.numpy()) <= 1e-3, b
+    # explicit per-call noise (the `noise=` argument) incl. per-sample maps
+    rng = np.random.Generator(np.random.PCG64(9))
+    wplus = orc.seeded_wplus(sd, 2, G.n_latent, seed=77)
+    noise = [T(rng.standard_normal((2 if i % 2 else 1, 1, 4 << ((i + 1) // 2), 4 << ((i + 1) // 2)), dtype=np.float32))
+             for i in range(G.num_layers)]
+    with torch.no_grad():
+        img = G([wplus.cuda()], input_is_latent=True, noise=[n.cuda() for n in noise])[0]
+        ref, _ = orc.generator_forward(sd, [wplus], size, cm, input_is_latent=True, noise=noise)
+        assert err(img, ref.numpy()) <= 1e-3
+        r1 = G([wplus.cuda()], input_is_latent=True, randomize_noise=True)[0]
+        r2 = G([wplus.cuda()], input_is_latent=True, randomize_noise=True)[0]
+    assert not torch.equal(r1, r2)
+
+
+def test_reenact_forward_golden(pkg, golden):
+    g = golden('reenact_32.npz')
+    size, cm, seed, batch = [int(v) for v in g['cfg']]
+    sd = orc.seeded_state_dict(size, cm, seed=seed)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=4).cuda()
+    with torch.no_grad():
+        A.linear.weight.copy_(cuda(g['A_w']))
+        A.linear.bias.copy_(cuda(g['A_b']))
+        shift = A(cuda(g['dp']))
+        assert err(shift, g['shift']) <= 1e-5
+        wsrc = cuda(g['wsrc'])
+        keep = wsrc.clone()
+        img, lat = pkg.generate_image(G, wsrc, 0.7, cuda(g['trunc']), w_plus=True, num_layers_shift=4,
+                                      shift_code=shift, input_is_latent=True, return_latents=True)
+        assert torch.equal(wsrc, keep)                      # caller's code is not mutated (generic.py:122)
+    assert err(lat, g['lat']) <= 1e-5
+    assert err(img, g['img']) <= 1e-3
+
+
+def test_weight_cache_invalidation(pkg):
+    size, cm = 8, 2
+    sd = orc.seeded_state_dict(size, cm, seed=8)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, 2, G.n_latent, seed=3)
+    with torch.no_grad():
+        a = G([wplus.cuda()], input_is_latent=True)[0]
+        G.convs[1].conv.weight.mul_(1.5)                    # in-place update (what Adam in optimize_g does)
+        sd2 = {k: v.cpu() for k, v in G.state_dict().items()}
+        b = G([wplus.cuda()], input_is_latent=True)[0]
+        ref, _ = orc.generator_forward(sd2, [wplus], size, cm, input_is_latent=True)
+    assert not torch.equal(a, b)
+    assert err(b, ref.numpy()) <= 1e-3
