@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: 256^2 reenacted frames/sec (BASELINE.json `metric`) and ModulatedConv2d TFLOP/s vs peak.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config the frames/sec metric is quoted on): self-reenactment of one source
+latent by synthetic driving parameters — per step and per GPU a batch of 32 driving vectors dp ~ U(-3,3)^15 ->
+shift = A(dp) (PyTorch) -> generate_image(G, w_src, truncation 0.7, trunc, shift) with G = Generator(256, 512, 8,
+channel_multiplier=1), random-init weights of the reference's shapes (no checkpoints offline).  Frames shard over ranks
+with no collective, so scaling is weak.
+
+  value      frames/s with dp already resident in HBM (device timed, CUDA events, max over ranks)
+  e2e        same through the public API with dp in PINNED HOST memory: H2D of dp and D2H of the fp32 frames inside the
+             timed region every step
+  roofline   the tcgen05 modconv kernel: algorithmic 3x3-conv FLOPs of the launches of one step / their summed
+             CUDA-event durations (events recorded by libsgr around each launch on the launching stream), against the
+             measured bf16 dense peak.  fp32 parity costs 3 bf16 MMAs per product (bf16x3): issued = 3 x algorithmic
+             for plain layers and 12 x for the polyphase up-layers; both numbers are reported.
+  cpu_baseline  the oracle port (oracle/stylegan2_oracle.py, torch-CPU) on the host cores, bounded sample.
+`--impl reference` times that same CPU implementation as the reference arm (the reference itself is Python and does
+not travel to the GPU box; its generator arithmetic is the torch-CPU conv the oracle calls).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE, CM, BATCH = 256, 1, 32
+METRIC = '256x256 reenacted frames/sec'
+WORKLOAD = ('configs[2] self-reenactment: 1 source W+ + synthetic driving dp, batch 32 per GPU, Generator(256,cm=1), '
+            'A(dp) shift on rows 0..7 + truncation 0.7 + full synthesis')
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {'bf16': float(d.get('bf16_tflops_sustained', d.get('bf16_tflops'))), 'bf16_burst': float(d.get('bf16_tflops')),
+                'hbm': float(d.get('hbm_gbs')), 'src': 'MEASURED_PEAKS.json (sustained)'}
+    except Exception:
+        return {'bf16': 1590.0, 'bf16_burst': 1590.0, 'hbm': 6650.0, 'src': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def conv_flops_per_frame():
+    """Algorithmic 3x3 modconv FLOPs per frame, per styled layer."""
+    from oracle import stylegan2_oracle as orc
+    channels, log_size, _, _ = orc.synthesis_config(SIZE, CM)
+    fl = [2 * 512 * 512 * 9 * 16]
+    cin = 512
+    for i in range(3, log_size + 1):
+        cout = channels[2 ** i]
+        fl.append(2 * cin * cout * 9 * (2 ** (i - 1)) ** 2)      # up layer at input resolution
+        fl.append(2 * cout * cout * 9 * (2 ** i) ** 2)
+        cin = cout
+    return fl
+
+
+def build_problem(device, rank):
+    import torch
+    from oracle import stylegan2_oracle as orc
+    import stylegan_directions_face_reenactment_b200 as pkg
+    sd = orc.seeded_state_dict(SIZE, CM, seed=0)
+    G = pkg.Generator(SIZE, 512, 8, channel_multiplier=CM)
+    G.load_state_dict(sd, strict=True)
+    G = G.to(device).eval()
+    torch.manual_seed(5)
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=8).to(device)
+    torch.manual_seed(7)
+    trunc = G.mean_latent(4096).detach()
+    wsrc = orc.seeded_wplus(sd, 1, G.n_latent, seed=11).to(device).repeat(BATCH, 1, 1)
+    g = torch.Generator().manual_seed(4321 + rank)
+    dp_host = [(torch.rand(BATCH, 15, generator=g) * 6 - 3).pin_memory() for _ in range(4)]
+    return pkg, sd, G, A, trunc, wsrc, dp_host
+
+
+def cpu_generator_fps(sd, batch, repeats, threads):
+    """Oracle port on the host cores: frames/s of generate_image at `batch` (bounded sample)."""
+    import torch
+    from oracle import stylegan2_oracle as orc
+    torch.set_num_threads(threads)
+    n_latent = orc.synthesis_config(SIZE, CM)[3]
+    w = orc.seeded_wplus(sd, batch, n_latent, seed=99)
+    trunc = w[:1, 0]
+    shift = 0.1 * torch.ones(batch, 8, 512)
+    best = None
+    with torch.no_grad():
+        for i in range(repeats + 1):
+            t0 = time.perf_counter()
+            orc.generate_image(sd, w, 0.7, trunc, SIZE, CM, shift_code=shift)
+            dt = time.perf_counter() - t0
+            if i > 0:
+                best = dt if best is None else min(best, dt)
+    return batch / best
+
+
+def run_reference(args, rank):
+    """Reference arm: the path's CPU implementation (oracle port) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import stylegan2_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = orc.seeded_state_dict(SIZE, CM, seed=0)
+    sample = 4
+    n_latent = orc.synthesis_config(SIZE, CM)[3]
+    w = orc.seeded_wplus(sd, 1, n_latent, seed=11).repeat(sample, 1, 1)
+    trunc = w[:1, 0]
+    g = torch.Generator().manual_seed(4321)
+    aw = 0.03 * torch.randn(4096, 15, generator=g)
+    ab = torch.zeros(4096)
+
+    def step():
+        dp = torch.rand(sample, 15, generator=g) * 6 - 3
+        shift = orc.direction_matrix_forward(aw, ab, dp, 512, 8)
+        orc.generate_image(sd, w, 0.7, trunc, SIZE, CM, shift_code=shift)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sample': '%d frames per step of the same workload' % sample},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d steps x %d frames, torch-CPU oracle port of the reference generator' % (args.steps, sample)},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-baseline', type=int, default=1)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        args.steps = min(args.steps, 8)
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+
+    pkg, sd, G, A, trunc, wsrc, dp_host = build_problem(device, rank)
+    from stylegan_directions_face_reenactment_b200 import _native
+    lib = _native.lib()
+    dp_dev = [d.to(device) for d in dp_host]
+
+    def step_resident(i):
+        with torch.no_grad():
+            shift = A(dp_dev[i % len(dp_dev)])
+            return pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=shift,
+                                      input_is_latent=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, finish=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        if finish is not None:
+            finish()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.sgr_reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = lib.sgr_launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    frames = BATCH * world * args.steps
+    value = frames / (ms * 1e-3)
+
+    # ---- end to end: dp from pinned host memory, frames back to pinned host memory, every step
+    out_host = [torch.empty(BATCH, 3, SIZE, SIZE).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=device)
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def step_e2e(i):
+        with torch.no_grad():
+            dp = dp_host[i % len(dp_host)].to(device, non_blocking=True)
+            img = pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
+                                     input_is_latent=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            out_host[slot].copy_(img, non_blocking=True)
+            img.record_stream(copy_stream)
+            done[slot].record(copy_stream)
+
+    def finish_e2e():                                          # the last copies end inside the timed region
+        for ev in done:
+            torch.cuda.current_stream().wait_event(ev)
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps, finish_e2e)
+    e2e_value = frames / (ms_e2e * 1e-3)
+
+    # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch)
+    roofline, layers = None, None
+    if rank == 0:
+        prof_steps = min(args.steps, 10)
+        lib.sgr_profile_enable(1)
+        lib.sgr_profile_collect(None, 0)
+        for i in range(prof_steps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 8192)()
+        n = lib.sgr_profile_collect(buf, 8192)
+        lib.sgr_profile_enable(0)
+        per_step = n // prof_steps
+        fl = conv_flops_per_frame()
+        assert per_step == len(fl), (per_step, len(fl))
+        dur = [sum(buf[s * per_step + l] for s in range(prof_steps)) / prof_steps for l in range(per_step)]   # ms
+        pk = peaks()
+        total_ms = sum(dur)
+        total_fl = sum(fl) * BATCH
+        achieved = total_fl / (total_ms * 1e-3) / 1e12
+        issue_mult = [12 if l % 2 == 1 else 3 for l in range(per_step)]       # up layers: 4 phases x bf16x3
+        issued = sum(f * m for f, m in zip(fl, issue_mult)) * BATCH / (total_ms * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': 'modconv_kernel (13 launches/step)', 'achieved': achieved,
+                    'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'], 'traffic': None,
+                    'issued_tflops': issued, 'issued_frac': issued / pk['bf16'], 'peak_source': pk['src'],
+                    'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps)}
+        layers = [{'layer': l, 'ms': round(d, 4), 'algo_tflops': round(f * BATCH / (d * 1e-3) / 1e12, 2)}
+                  for l, (d, f) in enumerate(zip(dur, fl))]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        threads = os.cpu_count() or 1
+        fps = cpu_generator_fps(sd, 4, 2, threads)
+        cpu_baseline = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                        'sample': 'best of 2 x 4 frames after 1 warm-up, torch-CPU oracle port (generate_image, 256^2 cm=1)'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate)', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'size': SIZE, 'channel_multiplier': CM,
+                           'l2': 'inputs larger than L2: ~2 GB of activations stream per step',
+                           'parallelism': 'frames sharded over %d rank(s), no collective' % world},
+                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': BATCH * 15 * 4,
+                        'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE * 4, 'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+                'layers': layers}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

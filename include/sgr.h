@@ -36,6 +36,12 @@ const char* sgr_last_error(void);
 long long sgr_launch_count(void);
 void sgr_reset_launch_count(void);
 
+/* Per-launch timing of the modconv kernel (bench.py's roofline): while enabled, every sgr_modconv_forward records a
+ * CUDA event pair on its stream around the launch.  sgr_profile_collect synchronises on the recorded events, writes up
+ * to `cap` durations (milliseconds, launch order) and clears the list; returns the number of launches recorded. */
+void sgr_profile_enable(int on);
+int sgr_profile_collect(float* ms, int cap);
+
 /* ---------------------------------------------------------------------------------------------------------
  * upfirdn2d: zero-insert upsample x`up`, pad (pad0 before / pad1 after, negative crops), true 2-D convolution
  * with taps[kh][kw], decimate x`down`.  Replaces op/upfirdn2d.cpp:16-26 + op/upfirdn2d_kernel.cu:52-272

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
       const int b = tc.tb * p.bb + bl;
       const int y = tc.ty * p.bh + yy;
       const int x = tc.tx * p.bw + xx;
-      const bool valid = b < p.B;
+      const bool valid = b < p.B && y < p.H && x < p.W;     // partial tiles: TMA zero-fills, stores are masked
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -361,14 +361,19 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
 
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   if (!a || !a->x_c8 || !a->w_packed) {
     set_error("modconv: null input");
     return 1;
   }
-  if (a->batch <= 0 || !is_pow2(a->h_in) || !is_pow2(a->w_in) || a->h_in < 4 || a->w_in < 4) {
-    set_error("modconv: unsupported geometry B=%d H=%d W=%d (power-of-two sizes >= 4)", a->batch, a->h_in, a->w_in);
+  if (a->batch <= 0 || a->h_in < 1 || a->w_in < 1 || a->h_in > 16384 || a->w_in > 16384) {
+    set_error("modconv: unsupported geometry B=%d H=%d W=%d", a->batch, a->h_in, a->w_in);
     return 1;
   }
   if (a->cin % kBlockK != 0 || !is_pow2(a->cout) || a->cout < 32 || (a->ksize != 3 && a->ksize != 1)) {
@@ -391,11 +396,11 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->B = a->batch;
   p->H = a->h_in;
   p->W = a->w_in;
-  p->bw = std::min(a->w_in, 16);
-  p->bh = std::min(a->h_in, kTileM / p->bw);
+  p->bw = std::min(next_pow2(a->w_in), 16);
+  p->bh = std::min(next_pow2(a->h_in), kTileM / p->bw);
   p->bb = kTileM / (p->bw * p->bh);
-  p->tiles_x = a->w_in / p->bw;
-  p->tiles_y = a->h_in / p->bh;
+  p->tiles_x = (a->w_in + p->bw - 1) / p->bw;
+  p->tiles_y = (a->h_in + p->bh - 1) / p->bh;
   p->tiles_b = (a->batch + p->bb - 1) / p->bb;
   p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
   const int n_total = a->cout * (a->up ? 4 : 1);

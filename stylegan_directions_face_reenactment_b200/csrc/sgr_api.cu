@@ -26,6 +26,27 @@ bool check_launch(const char* what) {
   return true;
 }
 
+// ---- optional per-launch event timing of the modconv kernel
+static bool g_prof_on = false;
+static const int kProfCap = 8192;
+static cudaEvent_t g_prof_ev[kProfCap][2];
+static int g_prof_made = 0, g_prof_n = 0;
+
+static bool prof_begin(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= kProfCap) return false;
+  while (g_prof_made <= g_prof_n) {
+    cudaEventCreate(&g_prof_ev[g_prof_made][0]);
+    cudaEventCreate(&g_prof_ev[g_prof_made][1]);
+    ++g_prof_made;
+  }
+  cudaEventRecord(g_prof_ev[g_prof_n][0], st);
+  return true;
+}
+static void prof_end(cudaStream_t st) {
+  cudaEventRecord(g_prof_ev[g_prof_n][1], st);
+  ++g_prof_n;
+}
+
 static bool have_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -165,7 +186,24 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   if (conv_fill_params(args, &p, &nt)) return 1;
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
-  return launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+  const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
+  const int rc = launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+  if (prof) prof_end(static_cast<cudaStream_t>(stream));
+  return rc;
+}
+
+void sgr_profile_enable(int on) { g_prof_on = on != 0; }
+
+int sgr_profile_collect(float* ms, int cap) {
+  const int n = g_prof_n;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventSynchronize(g_prof_ev[i][1]);
+    cudaEventElapsedTime(&t, g_prof_ev[i][0], g_prof_ev[i][1]);
+    if (ms && i < cap) ms[i] = t;
+  }
+  g_prof_n = 0;
+  return n;
 }
 
 int sgr_style_affine(const float* latent, int latent_stride, int batch, const float* mod_weight, const float* mod_bias,
