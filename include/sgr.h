@@ -122,6 +122,7 @@ int sgr_demod(const float* s, const float* wsq, int batch, int cin, int cout, fl
 typedef struct sgr_styled_layer {
   int cin, cout, up, latent_row;
   const void* w_packed;      /* forward operator, sgr_pack_modconv_weight(transpose=0) */
+  const void* w_packed_t;    /* adjoint operator (transpose=1); only sgr_synthesis_backward reads it, may be NULL otherwise */
   const float* wsq;          /* [cout,cin] */
   const float* mod_weight;   /* [cin,512] */
   const float* mod_bias;     /* [cin] */
@@ -138,6 +139,7 @@ typedef struct sgr_rgb_layer {
   const float* mod_bias;     /* [cin] */
   const float* bias;         /* [3] */
   const float* fir;          /* upsample.kernel [4,4] (NULL for to_rgb1) */
+  const float* fir_flipped;  /* flip(fir) in both axes, for the adjoint; only sgr_synthesis_backward reads it */
 } sgr_rgb_layer;
 
 typedef struct sgr_synthesis {
@@ -155,6 +157,15 @@ size_t sgr_synthesis_workspace_bytes(const sgr_synthesis* net, int batch);
  * feats: NULL, or n_styled device pointers (entries may be NULL) receiving each StyledConv output [B,cout,res,res]. */
 int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
                           size_t workspace_bytes, float* const* feats, void* stream);
+
+/* Gradient of sum(image * grad_image) with respect to `latent` (dlatent: [B,n_latent,512], overwritten).
+ * feats: the n_styled saved StyledConv outputs of the forward call (all required).  Replaces ATen autograd through
+ * F.conv2d / F.conv_transpose2d and the modulation graph (model.py:232-273) for the A-matrix training step
+ * (libs/trainer.py:177-189); generator weight gradients are not produced. */
+size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch);
+int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
+                           const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,13 +23,13 @@ class ConvArgs(C.Structure):
 
 class StyledLayer(C.Structure):
     _fields_ = [('cin', C.c_int), ('cout', C.c_int), ('up', C.c_int), ('latent_row', C.c_int),
-                ('w_packed', _fp), ('wsq', _fp), ('mod_weight', _fp), ('mod_bias', _fp), ('noise', _fp),
+                ('w_packed', _fp), ('w_packed_t', _fp), ('wsq', _fp), ('mod_weight', _fp), ('mod_bias', _fp), ('noise', _fp),
                 ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('act_bias', _fp)]
 
 
 class RgbLayer(C.Structure):
     _fields_ = [('cin', C.c_int), ('latent_row', C.c_int), ('weight', _fp), ('mod_weight', _fp), ('mod_bias', _fp),
-                ('bias', _fp), ('fir', _fp)]
+                ('bias', _fp), ('fir', _fp), ('fir_flipped', _fp)]
 
 
 class Synthesis(C.Structure):
@@ -55,6 +55,9 @@ SIGNATURES = {
     'sgr_style_affine': (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp]),
     'sgr_demod': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     'sgr_synthesis_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
+    'sgr_synthesis_backward_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
+    'sgr_synthesis_backward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, C.c_size_t,
+                                         _fp]),
     'sgr_synthesis_forward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, _fp, _fp, C.c_size_t, C.POINTER(_fp),
                                         _fp]),
 }

@@ -1,0 +1,454 @@
+// Backward of the synthesis network with respect to the W+ latent (the only gradient the A-matrix training of the
+// reference consumes: Adam steps A alone, libs/trainer.py:144,187-189).
+//
+// Per styled layer l (input a_{l-1}, style s_l, demod d_l, pre-activation t_l, output a_l = sqrt2*lrelu(t_l)):
+//   ga_l  = gx_{l+1} * s_{l+1}  +  sum_c grgb_r[c] * Wrgb[c,o]/sqrt(C) * s_rgb[b,o]        (next conv + ToRGB branches)
+//   gt_l  = ga_l * sqrt2 * (a_l > 0 ? 1 : 0.2)                     (op/fused_bias_act_kernel.cu:43, keyed on the OUTPUT)
+//   gz_l  = gt_l * d_l[b,o]                                          -> bf16 hi/lo C8 planes, operand of the dgrad GEMM
+//   q_l   = sum_p gt_l * (t_l - noise - bias)   ( = gd * d )         demodulation branch
+//   gx_l  = conv^T_l(gz_l)                                           tcgen05 kernel with the adjoint-packed shared weights
+//   ds_l  = sum_p a_{l-1} * gx_l  -  s_l * ((q_l * d_l^2) @ Wsq_l)   conv term + demod term
+//   dlatent[:, row_l] += ds_l @ Wm_l / sqrt(512)                     EqualLinear modulation backward
+// No per-sample weight gradient is ever formed; generator weight gradients (optimize_g) are out of this kernel set.
+#include <string.h>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+
+namespace sgr {
+
+struct BwdActParams {
+  int B, C, H, W;
+  const float* gx;        // [B,C,H,W] dgrad output of the NEXT layer, or NULL
+  const float* s_next;    // [B,C] next layer's style (scale of gx)
+  const float* a;         // [B,C,H,W] saved forward output of this layer (batch stride a_bstride)
+  long long a_bstride;
+  const float* grgb;      // [B,3,H,W] or NULL
+  const float* wrgb;      // [3,C]
+  const float* s_rgb;     // [B,C]
+  const float* demod;     // [B,C]
+  const float* bias;      // [C]
+  const float* noise;     // [H,W] (+ batch stride)
+  long long noise_bstride;
+  const float* noise_w;
+  __nv_bfloat16* out_c8;  // gz planes or NULL
+  int s2d;
+  int act;                // 0: constant-input pseudo layer (only the ds reduction)
+  float* ds_next;         // [B,C] += sum_p a * gx
+  float* q;               // [B,C] += sum_p gt * (t - noise - bias)
+  float* ds_rgb;          // [B,C] += sum_p a * sum_c grgb*wrgb/sqrt(C)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// grid: (pixel groups, C/8, B); each thread: 4 consecutive pixels x 8 channels.
+__global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
+  const int HW = p.H * p.W;
+  const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool valid = pix < HW;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 8;
+  const int lane = threadIdx.x & 31;
+  const float kSqrt2 = 1.4142135623730951f, kInvSqrt2 = 0.7071067811865476f;
+  float g3[3][4];
+  float nz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    if (p.grgb) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.grgb + (static_cast<size_t>(b) * 3 + c) * HW + pix));
+        g3[c][0] = g.x; g3[c][1] = g.y; g3[c][2] = g.z; g3[c][3] = g.w;
+      }
+    }
+    if (p.noise) {
+      const float nw = __ldg(p.noise_w);
+      const float4 n = __ldg(reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(b) * p.noise_bstride + pix));
+      nz[0] = nw * n.x; nz[1] = nw * n.y; nz[2] = nw * n.z; nz[3] = nw * n.w;
+    }
+  }
+  const float rs = rsqrtf(static_cast<float>(p.C));
+  __nv_bfloat16 hi[4][8], lo[4][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    float dsn = 0.f, qa = 0.f, dsr = 0.f;
+    if (valid) {
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(b) * p.a_bstride +
+                                                               static_cast<size_t>(c) * HW + pix));
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.gx) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gx + (static_cast<size_t>(b) * p.C + c) * HW + pix));
+        gxv[0] = g.x; gxv[1] = g.y; gxv[2] = g.z; gxv[3] = g.w;
+      }
+      const float sn = p.gx ? __ldg(p.s_next + static_cast<size_t>(b) * p.C + c) : 0.f;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, sr = 0.f;
+      if (p.grgb) {
+        w0 = __ldg(p.wrgb + c) * rs;
+        w1 = __ldg(p.wrgb + p.C + c) * rs;
+        w2 = __ldg(p.wrgb + 2 * p.C + c) * rs;
+        sr = __ldg(p.s_rgb + static_cast<size_t>(b) * p.C + c);
+      }
+      const float d = p.act ? __ldg(p.demod + static_cast<size_t>(b) * p.C + c) : 1.f;
+      const float bi = (p.act && p.bias) ? __ldg(p.bias + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = av[j];
+        float ga = gxv[j] * sn;
+        dsn = fmaf(a, gxv[j], dsn);
+        if (p.grgb) {
+          const float r = fmaf(g3[0][j], w0, fmaf(g3[1][j], w1, g3[2][j] * w2));
+          ga = fmaf(r, sr, ga);
+          dsr = fmaf(a, r, dsr);
+        }
+        if (p.act) {
+          const bool pos = a > 0.f;
+          const float gt = ga * (pos ? kSqrt2 : 0.2f * kSqrt2);
+          const float t = pos ? a * kInvSqrt2 : a * (5.f * kInvSqrt2);
+          qa = fmaf(gt, t - nz[j] - bi, qa);
+          split_bf16(gt * d, hi[j][e], lo[j][e]);
+        }
+      }
+    }
+    dsn = warp_sum(dsn);
+    if (p.act) qa = warp_sum(qa);
+    if (p.grgb) dsr = warp_sum(dsr);
+    if (lane == 0) {
+      const size_t o = static_cast<size_t>(b) * p.C + c;
+      if (p.ds_next && p.gx) atomicAdd(p.ds_next + o, dsn);
+      if (p.act) atomicAdd(p.q + o, qa);
+      if (p.grgb) atomicAdd(p.ds_rgb + o, dsr);
+    }
+  }
+  if (valid && p.out_c8 && p.act) {
+    const int y = pix / p.W, x = pix % p.W;
+    const int chunks = p.C / 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      size_t off, plane;
+      if (!p.s2d) {
+        off = ((static_cast<size_t>(b) * chunks + blockIdx.y) * p.H + y) * p.W + x + j;
+        plane = static_cast<size_t>(p.B) * chunks * HW;
+      } else {
+        const int phase = (y & 1) * 2 + ((x + j) & 1);
+        const int H2 = p.H / 2, W2 = p.W / 2;
+        off = ((static_cast<size_t>(b) * (4 * chunks) + phase * chunks + blockIdx.y) * H2 + (y >> 1)) * W2 + ((x + j) >> 1);
+        plane = static_cast<size_t>(p.B) * chunks * HW;      // 4*chunks * H2*W2 == chunks * HW
+      }
+      uint4 h, l;
+      h.x = pack_bf16x2(hi[j][0], hi[j][1]); h.y = pack_bf16x2(hi[j][2], hi[j][3]);
+      h.z = pack_bf16x2(hi[j][4], hi[j][5]); h.w = pack_bf16x2(hi[j][6], hi[j][7]);
+      l.x = pack_bf16x2(lo[j][0], lo[j][1]); l.y = pack_bf16x2(lo[j][2], lo[j][3]);
+      l.z = pack_bf16x2(lo[j][4], lo[j][5]); l.w = pack_bf16x2(lo[j][6], lo[j][7]);
+      uint4* o4 = reinterpret_cast<uint4*>(p.out_c8);
+      o4[off] = h;
+      o4[plane + off] = l;
+    }
+  }
+}
+
+static int bwd_act_launch(const BwdActParams& p, cudaStream_t st) {
+  const int HW = p.H * p.W;
+  dim3 grid((HW / 4 + 127) / 128, p.C / 8, p.B);
+  bwd_act_kernel<<<grid, 128, 0, st>>>(p);
+  count_launch();
+  return check_launch("bwd_act_kernel") ? 0 : 1;
+}
+
+// ds[b,i] = ds_conv[b,i] - s[b,i] * sum_o q[b,o] d[b,o]^2 wsq[o,i]      (in place on ds_conv)
+struct DsJob {
+  float* ds;            // [B,cin] in/out
+  const float* s;       // [B,cin]
+  const float* q;       // [B,cout]
+  const float* d;       // [B,cout]
+  const float* wsq;     // [cout,cin]
+  int cin, cout;
+};
+struct DsJobs {
+  DsJob job[SGR_MAX_STYLED];
+  int n;
+};
+__global__ void ds_finish_kernel(const DsJobs jobs) {
+  const DsJob& j = jobs.job[blockIdx.z];
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float qd[512];
+  for (int o = threadIdx.x; o < j.cout; o += blockDim.x) {
+    const float d = j.d[static_cast<size_t>(b) * j.cout + o];
+    qd[o] = j.q[static_cast<size_t>(b) * j.cout + o] * d * d;
+  }
+  __syncthreads();
+  if (i >= j.cin) return;
+  float acc = 0.f;
+  for (int o = 0; o < j.cout; ++o) acc = fmaf(qd[o], __ldg(j.wsq + static_cast<size_t>(o) * j.cin + i), acc);
+  const size_t k = static_cast<size_t>(b) * j.cin + i;
+  j.ds[k] = j.ds[k] - j.s[k] * acc;
+}
+
+// dlatent[b,row,k] += sum_i ds[b,i] * Wm[i,k] / sqrt(512)
+struct LatJob {
+  const float* ds;      // [B,cin]
+  const float* wm;      // [cin,512]
+  int cin, row;
+};
+struct LatJobs {
+  LatJob job[SGR_MAX_STYLED + SGR_MAX_RGB];
+  int n;
+};
+__global__ void dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, int latent_stride) {
+  const LatJob& j = jobs.job[blockIdx.z];
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;       // 0..511
+  __shared__ float dsv[512];
+  for (int i = threadIdx.x; i < j.cin; i += blockDim.x) dsv[i] = j.ds[static_cast<size_t>(b) * j.cin + i];
+  __syncthreads();
+  float acc = 0.f;
+  for (int i = 0; i < j.cin; ++i) acc = fmaf(dsv[i], __ldg(j.wm + static_cast<size_t>(i) * SGR_STYLE_DIM + k), acc);
+  atomicAdd(dlatent + static_cast<size_t>(b) * latent_stride + static_cast<size_t>(j.row) * SGR_STYLE_DIM + k,
+            acc * 0.044194173824159216f);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BwdPlan {
+  size_t style_off[SGR_MAX_STYLED], rgbstyle_off[SGR_MAX_RGB], demod_off[SGR_MAX_STYLED];
+  size_t s2_off, coef_off;                       // scratch outputs of the table kernel (unused by backward)
+  size_t ds_off[SGR_MAX_STYLED], q_off[SGR_MAX_STYLED], dsrgb_off[SGR_MAX_RGB];
+  size_t acc_begin, acc_end;
+  size_t grgb_off[SGR_MAX_RGB];
+  size_t gz_off, gx_off[2];
+  size_t total;
+};
+
+static int plan_backward(const sgr_synthesis* net, int batch, BwdPlan* pl) {
+  if (!net || batch <= 0 || net->n_styled < 1 || net->n_styled > SGR_MAX_STYLED || net->n_styled != 2 * net->n_rgb - 1) {
+    set_error("synthesis_backward: bad network descriptor");
+    return 1;
+  }
+  const size_t B = static_cast<size_t>(batch);
+  size_t off = 0, cmax = 0;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    pl->style_off[l] = off; off = align_up(off + B * L.cin * 4, 256);
+    pl->demod_off[l] = off; off = align_up(off + B * L.cout * 4, 256);
+    cmax = cmax > static_cast<size_t>(L.cout) ? cmax : L.cout;
+  }
+  for (int r = 0; r < net->n_rgb; ++r) {
+    pl->rgbstyle_off[r] = off; off = align_up(off + B * net->rgb[r].cin * 4, 256);
+  }
+  pl->s2_off = off; off = align_up(off + B * cmax * 4, 256);
+  pl->coef_off = off; off = align_up(off + B * 3 * cmax * 4, 256);
+  pl->acc_begin = off;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const sgr_styled_layer& L = net->styled[l];
+    pl->ds_off[l] = off; off = align_up(off + B * L.cin * 4, 256);
+    pl->q_off[l] = off; off = align_up(off + B * L.cout * 4, 256);
+  }
+  for (int r = 0; r < net->n_rgb; ++r) {
+    pl->dsrgb_off[r] = off; off = align_up(off + B * net->rgb[r].cin * 4, 256);
+  }
+  pl->acc_end = off;
+  size_t max_out = 0, max_in = 0;
+  for (int r = 0; r < net->n_rgb; ++r) {
+    const size_t res = static_cast<size_t>(4) << r;
+    pl->grgb_off[r] = off; off = align_up(off + B * 3 * res * res * 4, 256);
+  }
+  for (int l = 0; l < net->n_styled; ++l) {
+    const size_t res_out = static_cast<size_t>(4) << ((l + 1) / 2);
+    const size_t res_in = net->styled[l].up ? res_out / 2 : res_out;
+    const size_t eo = B * net->styled[l].cout * res_out * res_out;
+    const size_t ei = B * net->styled[l].cin * res_in * res_in;
+    max_out = max_out > eo ? max_out : eo;
+    max_in = max_in > ei ? max_in : ei;
+  }
+  pl->gz_off = off; off = align_up(off + max_out * 4, 256);
+  for (int i = 0; i < 2; ++i) {
+    pl->gx_off[i] = off; off = align_up(off + max_in * 4, 256);
+  }
+  pl->total = off;
+  return 0;
+}
+
+}  // namespace sgr
+
+using namespace sgr;
+
+extern "C" {
+
+size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch) {
+  BwdPlan pl;
+  if (plan_backward(net, batch, &pl)) return 0;
+  return pl.total;
+}
+
+int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
+                           const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libsgr has no CPU fallback");
+    return 1;
+  }
+  BwdPlan pl;
+  if (plan_backward(net, batch, &pl)) return 1;
+  if (!latent || !feats || !grad_image || !dlatent || !workspace || workspace_bytes < pl.total ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("synthesis_backward: null pointer, unaligned or too small workspace (%zu < %zu)", workspace_bytes, pl.total);
+    return 1;
+  }
+  for (int l = 0; l < net->n_styled; ++l)
+    if (!feats[l] || !net->styled[l].w_packed_t) {
+      set_error("synthesis_backward: layer %d lacks its saved activation or adjoint-packed weights", l);
+      return 1;
+    }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int latent_stride = net->n_latent * SGR_STYLE_DIM;
+  const int L = net->n_styled, R = net->n_rgb;
+
+  // styles + demod (recomputed: cheaper than keeping them alive between forward and backward)
+  StyleJobs sj;
+  sj.n = 0;
+  for (int l = 0; l < L; ++l)
+    sj.job[sj.n++] = StyleJob{net->styled[l].mod_weight, net->styled[l].mod_bias, F(pl.style_off[l]), net->styled[l].cin,
+                              net->styled[l].latent_row};
+  for (int r = 0; r < R; ++r)
+    sj.job[sj.n++] = StyleJob{net->rgb[r].mod_weight, net->rgb[r].mod_bias, F(pl.rgbstyle_off[r]), net->rgb[r].cin,
+                              net->rgb[r].latent_row};
+  if (style_jobs_launch(sj, latent, latent_stride, batch, st)) return 1;
+  TableJobs tj;
+  tj.n = L;
+  for (int l = 0; l < L; ++l) {
+    TableJob& j = tj.job[l];
+    memset(&j, 0, sizeof(j));
+    j.s = F(pl.style_off[l]);
+    j.wsq = net->styled[l].wsq;
+    j.demod = F(pl.demod_off[l]);
+    j.s2 = F(pl.s2_off);
+    j.rgb_coef = F(pl.coef_off);
+    j.cin = net->styled[l].cin;
+    j.cout = net->styled[l].cout;
+  }
+  if (table_jobs_launch(tj, batch, st)) return 1;
+  if (cudaMemsetAsync(ws + pl.acc_begin, 0, pl.acc_end - pl.acc_begin, st) != cudaSuccess ||
+      cudaMemsetAsync(dlatent, 0, static_cast<size_t>(batch) * latent_stride * 4, st) != cudaSuccess) {
+    set_error("synthesis_backward: memset failed");
+    return 1;
+  }
+
+  // gradient of every ToRGB output: grgb_R = gimage; grgb_{r-1} = adjoint of the 2x FIR upsample of the skip
+  // (upfirdn2d with flipped taps, down 2, pad (1,1); op/upfirdn2d.py:32-43,112-117)
+  const float* grgb[SGR_MAX_RGB];
+  grgb[R - 1] = grad_image;
+  for (int r = R - 1; r >= 1; --r) {
+    const int res = 4 << r;
+    // sgr upfirdn2d applies the TRUE convolution with its taps, so the adjoint needs the flipped FIR
+    if (!net->rgb[r].fir_flipped) {
+      set_error("synthesis_backward: rgb %d lacks fir_flipped", r);
+      return 1;
+    }
+    if (upfirdn2d_launch(grgb[r], F(pl.grgb_off[r - 1]), net->rgb[r].fir_flipped, batch * 3, res, res, 1, 2, 1, 1, 4, 4, st))
+      return 1;
+    grgb[r - 1] = F(pl.grgb_off[r - 1]);
+  }
+
+  // layer chain, last to first
+  const float* gx_next = nullptr;      // dgrad output of layer l+1 == gradient wrt (a_l * s_{l+1})
+  int gx_cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const sgr_styled_layer& Ly = net->styled[l];
+    const int res_out = 4 << ((l + 1) / 2);
+    const int res_in = Ly.up ? res_out / 2 : res_out;
+    const int r = (l + 1) / 2;
+    BwdActParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = batch; p.C = Ly.cout; p.H = res_out; p.W = res_out;
+    p.gx = gx_next;
+    p.s_next = gx_next ? F(pl.style_off[l + 1]) : nullptr;
+    p.a = feats[l];
+    p.a_bstride = static_cast<long long>(Ly.cout) * res_out * res_out;
+    if (!Ly.up) {
+      p.grgb = grgb[r];
+      p.wrgb = net->rgb[r].weight;
+      p.s_rgb = F(pl.rgbstyle_off[r]);
+      p.ds_rgb = F(pl.dsrgb_off[r]);
+    }
+    p.demod = F(pl.demod_off[l]);
+    p.bias = Ly.act_bias;
+    p.noise = Ly.noise;
+    p.noise_bstride = Ly.noise_batch_stride;
+    p.noise_w = Ly.noise_weight;
+    p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
+    p.s2d = Ly.up;
+    p.act = 1;
+    p.ds_next = gx_next ? F(pl.ds_off[l + 1]) : nullptr;
+    p.q = F(pl.q_off[l]);
+    if (bwd_act_launch(p, st)) return 1;
+
+    // data gradient through the shared-weight convolution (adjoint-packed weights)
+    sgr_conv_args a;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch;
+    a.cin = Ly.up ? 4 * Ly.cout : Ly.cout;
+    a.cout = Ly.cin;
+    a.h_in = res_in;
+    a.w_in = res_in;
+    a.ksize = 3;
+    a.up = 0;
+    a.act = 0;
+    a.act_gain = 1.f;
+    a.x_c8 = ws + pl.gz_off;
+    a.w_packed = Ly.w_packed_t;
+    a.out_f32 = F(pl.gx_off[gx_cur]);
+    if (sgr_modconv_forward(&a, stream)) return 1;
+    gx_next = F(pl.gx_off[gx_cur]);
+    gx_cur = 1 - gx_cur;
+  }
+  // conv term of ds_0: the input of conv1 is the constant 4x4 tensor (batch stride 0)
+  {
+    BwdActParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = batch; p.C = net->styled[0].cin; p.H = 4; p.W = 4;
+    p.gx = gx_next;
+    p.s_next = F(pl.style_off[0]);
+    p.a = net->const_input;
+    p.a_bstride = 0;
+    p.act = 0;
+    p.ds_next = F(pl.ds_off[0]);
+    if (bwd_act_launch(p, st)) return 1;
+  }
+
+  // demodulation term, then the modulation linears back to the latent rows
+  DsJobs dj;
+  dj.n = L;
+  int cin_max = 0;
+  for (int l = 0; l < L; ++l) {
+    dj.job[l] = DsJob{F(pl.ds_off[l]), F(pl.style_off[l]), F(pl.q_off[l]), F(pl.demod_off[l]), net->styled[l].wsq,
+                      net->styled[l].cin, net->styled[l].cout};
+    cin_max = cin_max > net->styled[l].cin ? cin_max : net->styled[l].cin;
+    if (net->styled[l].cout > 512) {
+      set_error("synthesis_backward: cout > 512 unsupported");
+      return 1;
+    }
+  }
+  ds_finish_kernel<<<dim3((cin_max + 127) / 128, batch, L), 128, 0, st>>>(dj);
+  count_launch();
+  if (!check_launch("ds_finish_kernel")) return 1;
+  LatJobs lj;
+  lj.n = 0;
+  for (int l = 0; l < L; ++l)
+    lj.job[lj.n++] = LatJob{F(pl.ds_off[l]), net->styled[l].mod_weight, net->styled[l].cin, net->styled[l].latent_row};
+  for (int r = 0; r < R; ++r)
+    lj.job[lj.n++] = LatJob{F(pl.dsrgb_off[r]), net->rgb[r].mod_weight, net->rgb[r].cin, net->rgb[r].latent_row};
+  dlatent_kernel<<<dim3(SGR_STYLE_DIM / 128, batch, lj.n), 128, 0, st>>>(lj, dlatent, latent_stride);
+  count_launch();
+  return check_launch("dlatent_kernel") ? 0 : 1;
+}
+
+}  // extern "C"

@@ -18,8 +18,9 @@ def _f32c(t):
 class NetDescriptor:
     """Keeps the ctypes struct and every tensor it points to alive for the duration of a call."""
 
-    def __init__(self, g, noise, batch):
+    def __init__(self, g, noise, batch, backward=False):
         self.keep = []
+        self.noise_used = []
         s = N.Synthesis()
         styled = g.styled_layers()
         rgbs = g.rgb_layers()
@@ -32,6 +33,8 @@ class NetDescriptor:
             d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, int(conv.upsample)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
             d.w_packed, d.wsq = self._p(packed), self._p(wsq)
+            if backward:
+                d.w_packed_t = self._p(conv.packed(transpose=True)[0])
             d.mod_weight, d.mod_bias = self._p(conv.modulation.weight), self._p(conv.modulation.bias)
             nz = noise[l]
             res = 4 << ((l + 1) // 2)
@@ -39,6 +42,7 @@ class NetDescriptor:
                 nz = torch.randn(batch, 1, res, res, device=g.input.input.device)
             if nz.shape[-1] != res or nz.shape[-2] != res:
                 raise RuntimeError('noise %d has shape %s, expected [*,1,%d,%d]' % (l, tuple(nz.shape), res, res))
+            self.noise_used.append(nz)
             d.noise = self._p(nz)
             d.noise_batch_stride = res * res if (nz.shape[0] == batch and batch > 1) else 0
             d.noise_weight = self._p(layer.noise.weight)
@@ -51,6 +55,8 @@ class NetDescriptor:
             d.mod_weight, d.mod_bias = self._p(layer.conv.modulation.weight), self._p(layer.conv.modulation.bias)
             d.bias = self._p(layer.bias)
             d.fir = self._p(layer.upsample.kernel) if hasattr(layer, 'upsample') else None
+            if backward and hasattr(layer, 'upsample'):
+                d.fir_flipped = self._p(torch.flip(layer.upsample.kernel, [0, 1]))
         self.struct = s
 
     def _p(self, t):
@@ -59,15 +65,17 @@ class NetDescriptor:
         return N.ptr(t)
 
 
-def _workspace(g, desc, batch, device):
-    key = (batch, device.index)
+def _workspace(g, desc, batch, device, backward=False):
+    key = (batch, device.index, backward)
     ws = g._workspace.get(key)
     if ws is None:
-        nbytes = N.lib().sgr_synthesis_workspace_bytes(C.byref(desc.struct), batch)
+        fn = N.lib().sgr_synthesis_backward_workspace_bytes if backward else N.lib().sgr_synthesis_workspace_bytes
+        nbytes = fn(C.byref(desc.struct), batch)
         if nbytes == 0:
-            raise RuntimeError('sgr_synthesis_workspace_bytes: %s' % N.lib().sgr_last_error().decode())
+            raise RuntimeError('sgr workspace query: %s' % N.lib().sgr_last_error().decode())
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        g._workspace.clear()                           # one live workspace per generator
+        for k in [k for k in g._workspace if k[2] == backward]:     # one live workspace per direction
+            del g._workspace[k]
         g._workspace[key] = ws
     return ws
 
@@ -96,7 +104,7 @@ def synthesis_forward(g, latent, noise, want_feats):
             feat_ptrs = arr
         N.check(N.lib().sgr_synthesis_forward(C.byref(desc.struct), N.ptr(lat), batch, N.ptr(image), N.ptr(ws),
                                               ws.numel(), feat_ptrs, N.stream()), 'sgr_synthesis_forward')
-    return image, feats, lat
+    return image, feats, lat, desc.noise_used
 
 
 class _Synthesis(torch.autograd.Function):
@@ -104,9 +112,9 @@ class _Synthesis(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, latent, g, noise):
-        image, feats, lat = synthesis_forward(g, latent, noise, want_feats=True)
+        image, feats, lat, noise_used = synthesis_forward(g, latent, noise, want_feats=True)
         ctx.g = g
-        ctx.noise = noise
+        ctx.noise = noise_used
         ctx.save_for_backward(lat, *feats)
         return image
 
@@ -119,9 +127,9 @@ class _Synthesis(torch.autograd.Function):
 
 def run_synthesis(g, latent, noise, return_features=False):
     if return_features:
-        image, feats, _ = synthesis_forward(g, latent, noise, want_feats=True)
+        image, feats, _, _ = synthesis_forward(g, latent, noise, want_feats=True)
         return image, feats
     if torch.is_grad_enabled() and latent.requires_grad:
         return _Synthesis.apply(latent, g, noise)
-    image, _, _ = synthesis_forward(g, latent, noise, want_feats=False)
+    image, _, _, _ = synthesis_forward(g, latent, noise, want_feats=False)
     return image

@@ -249,3 +249,63 @@ def test_weight_cache_invalidation(pkg):
         ref, _ = orc.generator_forward(sd2, [wplus], size, cm, input_is_latent=True)
     assert not torch.equal(a, b)
     assert err(b, ref.numpy()) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------ backward (dL/dA)
+def test_reenact_dA_golden(pkg, golden):
+    """dL/dA through generate_image against the reference's own autograd (reenact_32.npz), rel <= 1e-3."""
+    g = golden('reenact_32.npz')
+    size, cm, seed, batch = [int(v) for v in g['cfg']]
+    sd = orc.seeded_state_dict(size, cm, seed=seed)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=4).cuda()
+    with torch.no_grad():
+        A.linear.weight.copy_(cuda(g['A_w']))
+        A.linear.bias.copy_(cuda(g['A_b']))
+    img = pkg.generate_image(G, cuda(g['wsrc']), 0.7, cuda(g['trunc']), w_plus=True, num_layers_shift=4,
+                             shift_code=A(cuda(g['dp'])), input_is_latent=True)
+    loss = (img * cuda(g['r'])).sum() / img.numel()
+    assert abs(loss.item() - float(g['loss'])) <= 1e-4 * max(1.0, abs(float(g['loss'])))
+    G.zero_grad()
+    loss.backward()
+    assert err(A.linear.weight.grad, g['gA_w']) <= 1e-3 * np.abs(g['gA_w']).max()
+    assert err(A.linear.bias.grad, g['gA_b']) <= 1e-3 * np.abs(g['gA_b']).max()
+    assert all(p.grad is None for p in G.parameters())       # frozen generator: no weight gradients are formed
+
+
+@pytest.mark.parametrize('size,cm,batch', [(8, 2, 2), (32, 2, 3), (256, 1, 2)])
+def test_dlatent_vs_oracle_autograd(pkg, size, cm, batch):
+    sd = orc.seeded_state_dict(size, cm, seed=12)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, batch, G.n_latent, seed=21)
+    rng = np.random.Generator(np.random.PCG64(3))
+    r = T(rng.standard_normal((batch, 3, size, size), dtype=np.float32))
+    wr = wplus.clone().requires_grad_(True)
+    ref, _ = orc.generator_forward(sd, [wr], size, cm, input_is_latent=True)
+    (ref * r).sum().backward()
+    wg = wplus.cuda().requires_grad_(True)
+    img, _ = G([wg], input_is_latent=True)
+    (img * r.cuda()).sum().backward()
+    gref = wr.grad.numpy()
+    scale = np.abs(gref).max()
+    for row in range(G.n_latent):                          # every latent row separately: each layer's style path
+        e = np.abs(wg.grad[:, row].cpu().numpy() - gref[:, row]).max()
+        assert e <= 2e-3 * scale, (row, e, scale)
+    assert err(wg.grad, gref) <= 2e-3 * scale
+
+
+def test_backward_with_randomized_noise_is_consistent(pkg):
+    """randomize_noise draws per-sample noise inside forward; backward must reuse exactly those maps."""
+    size, cm = 32, 2
+    sd = orc.seeded_state_dict(size, cm, seed=2)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    w = orc.seeded_wplus(sd, 2, G.n_latent, seed=1).cuda().requires_grad_(True)
+    img, _ = G([w], input_is_latent=True, randomize_noise=True)
+    img.square().mean().backward()
+    assert torch.isfinite(w.grad).all() and w.grad.abs().max() > 0
