@@ -30,6 +30,13 @@ extern "C" {
 #define SGR_MAX_RGB 12
 #define SGR_STYLE_DIM 512
 
+/* Operand formats of the split-precision tensor-core GEMM (3 MMAs per product either way):
+ *   SGR_FMT_BF16  bf16 hi/lo planes: 16 mantissa bits, fp32 range (~2e-5 relative)            — gradient GEMMs
+ *   SGR_FMT_FP16  fp16 hi/lo planes: 22 mantissa bits (~5e-7 relative); activations are stored x 2^-4 and weights
+ *                 x 2^8 inside the library and saturate at +-65504 (|activation * style| up to 1e6)  — forward pass */
+#define SGR_FMT_BF16 0
+#define SGR_FMT_FP16 1
+
 const char* sgr_version(void);
 const char* sgr_last_error(void);
 /* number of kernels of this library launched by the calling thread since the last reset (bench bookkeeping) */
@@ -69,14 +76,14 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
  */
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose);
 int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up,
-                            int transpose, void* packed, float* wsq, void* stream);
+                            int transpose, int format, void* packed, float* wsq, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Layout helpers (module-level calls and tests; the fused network path never needs them).
  * NCHW fp32 (optionally * scale[b,c]) -> C8 bf16 hi/lo planes; s2d != 0 additionally folds 2x2 pixel phases
  * into channels (channel = phase*C + c at half resolution), the layout the up-layer adjoint consumes. */
 int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, int channels, int h, int w, int s2d,
-                   void* stream);
+                   int format, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * One modulated convolution (ModulatedConv2d.forward + NoiseInjection + FusedLeakyReLU, model.py:232-287,331-337)
@@ -95,6 +102,8 @@ typedef struct sgr_conv_args {
   int up;                 /* 0: same resolution; 1: output is 2x (polyphase), cout phases packed by sgr_pack_modconv_weight */
   int act;                /* apply leaky-relu 0.2 */
   float act_gain;         /* sqrt(2) for StyledConv, 1 for raw conv */
+  int operand_format;     /* SGR_FMT_* of x_c8 and w_packed */
+  int out_format;         /* SGR_FMT_* written to out_c8 */
   const void* x_c8;       /* [2][B][cin/8][h_in][w_in][8] bf16 */
   const void* w_packed;
   const float* demod;     /* [B,cout] or NULL */
@@ -147,6 +156,7 @@ typedef struct sgr_synthesis {
   int n_styled;              /* conv1 + convs.* = 2*log2(size) - 3 */
   int n_rgb;                 /* to_rgb1 + to_rgbs.* = log2(size) - 1 */
   int n_latent;
+  int format;                /* SGR_FMT_* of the forward pass (w_packed of every layer must be packed with it) */
   const float* const_input;  /* [512,4,4] */
   sgr_styled_layer styled[SGR_MAX_STYLED];
   sgr_rgb_layer rgb[SGR_MAX_RGB];

@@ -9,13 +9,22 @@ LIB_PATH = os.path.join(_HERE, 'libsgr.so')
 MAX_STYLED = 24
 MAX_RGB = 12
 STYLE_DIM = 512
+FMT_BF16, FMT_FP16 = 0, 1
+
+
+def default_format():
+    """Forward operand format: fp16 hi/lo split (default) or bf16 hi/lo via SGR_PRECISION=bf16x3 (csrc/sgr_ptx.cuh)."""
+    v = os.environ.get('SGR_PRECISION', 'fp16x3').lower()
+    if v not in ('fp16x3', 'bf16x3'):
+        raise RuntimeError('SGR_PRECISION must be fp16x3 or bf16x3, got %r' % v)
+    return FMT_FP16 if v == 'fp16x3' else FMT_BF16
 
 _fp = C.c_void_p          # device pointers travel as integers
 
 
 class ConvArgs(C.Structure):
     _fields_ = [('batch', C.c_int), ('cin', C.c_int), ('cout', C.c_int), ('h_in', C.c_int), ('w_in', C.c_int),
-                ('ksize', C.c_int), ('up', C.c_int), ('act', C.c_int), ('act_gain', C.c_float),
+                ('ksize', C.c_int), ('up', C.c_int), ('act', C.c_int), ('act_gain', C.c_float), ('operand_format', C.c_int), ('out_format', C.c_int),
                 ('x_c8', _fp), ('w_packed', _fp), ('demod', _fp), ('bias', _fp), ('noise', _fp),
                 ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('s2', _fp), ('out_c8', _fp),
                 ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_acc', _fp)]
@@ -33,7 +42,7 @@ class RgbLayer(C.Structure):
 
 
 class Synthesis(C.Structure):
-    _fields_ = [('size', C.c_int), ('n_styled', C.c_int), ('n_rgb', C.c_int), ('n_latent', C.c_int),
+    _fields_ = [('size', C.c_int), ('n_styled', C.c_int), ('n_rgb', C.c_int), ('n_latent', C.c_int), ('format', C.c_int),
                 ('const_input', _fp), ('styled', StyledLayer * MAX_STYLED), ('rgb', RgbLayer * MAX_RGB)]
 
 
@@ -49,8 +58,8 @@ SIGNATURES = {
     'sgr_fused_bias_act': (C.c_int, [_fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                      C.c_float, _fp]),
     'sgr_packed_weight_bytes': (C.c_size_t, [C.c_int] * 5),
-    'sgr_pack_modconv_weight': (C.c_int, [_fp, _fp] + [C.c_int] * 5 + [_fp, _fp, _fp]),
-    'sgr_nchw_to_c8': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 5 + [_fp]),
+    'sgr_pack_modconv_weight': (C.c_int, [_fp, _fp] + [C.c_int] * 6 + [_fp, _fp, _fp]),
+    'sgr_nchw_to_c8': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 6 + [_fp]),
     'sgr_modconv_forward': (C.c_int, [C.POINTER(ConvArgs), _fp]),
     'sgr_style_affine': (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp]),
     'sgr_demod': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),

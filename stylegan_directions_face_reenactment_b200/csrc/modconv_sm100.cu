@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, NT);
+      const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
       constexpr uint32_t kALbo = kTileM * 16, kBLbo = NT * 16;
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 d4 = dptr ? __ldg(reinterpret_cast<const float4*>(dptr) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            d4.x *= p.acc_scale; d4.y *= p.acc_scale; d4.z *= p.acc_scale; d4.w *= p.acc_scale;
             float4 b4 = bptr ? __ldg(reinterpret_cast<const float4*>(bptr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             float t0 = fmaf(v[4 * q + 0], d4.x, nz + b4.x);
             float t1 = fmaf(v[4 * q + 1], d4.y, nz + b4.y);
@@ -233,19 +234,16 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(sptr) + 2 * q + 1);
                 g[0] = s0.x; g[1] = s0.y; g[2] = s0.z; g[3] = s0.w;
                 g[4] = s1.x; g[5] = s1.y; g[6] = s1.z; g[7] = s1.w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) g[e] *= p.out_scale;
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = p.act_gain;
+                for (int e = 0; e < 8; ++e) g[e] = p.act_gain * p.out_scale;
               }
               uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[8 * q + 2 * e] * g[2 * e], h0, l0);
-                split_bf16(v[8 * q + 2 * e + 1] * g[2 * e + 1], h1, l1);
-                hi[e] = pack_bf16x2(h0, h1);
-                lo[e] = pack_bf16x2(l0, l1);
-              }
+              for (int e = 0; e < 4; ++e)
+                split2(v[8 * q + 2 * e] * g[2 * e], v[8 * q + 2 * e + 1] * g[2 * e + 1], p.out_fmt, hi[e], lo[e]);
               *reinterpret_cast<uint4*>(optr + q * chunk_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(optr + plane_stride + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -414,6 +412,15 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->Wout = a->up ? 2 * a->w_in : a->w_in;
   p->act = a->act;
   p->act_gain = a->act_gain;
+  if ((a->operand_format != SGR_FMT_BF16 && a->operand_format != SGR_FMT_FP16) ||
+      (a->out_format != SGR_FMT_BF16 && a->out_format != SGR_FMT_FP16)) {
+    set_error("modconv: unknown operand format");
+    return 1;
+  }
+  p->fmt = a->operand_format;
+  p->acc_scale = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
+  p->out_fmt = a->out_format;
+  p->out_scale = act_scale(a->out_format);
   p->wpacked = static_cast<const __nv_bfloat16*>(a->w_packed);
   p->demod = a->demod;
   p->bias = a->bias;

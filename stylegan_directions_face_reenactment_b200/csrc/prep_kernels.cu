@@ -56,7 +56,7 @@ __device__ float effective_weight(const float* __restrict__ w, const float* __re
 // packed layout: [n_tile][tap][kc][plane][chunk(4)][n_local(NT)][8]
 __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ fir, int cout, int cin,
                                    int ks, int up, int transpose, int n_total, int k_total, int nt, float scale,
-                                   __nv_bfloat16* __restrict__ packed) {
+                                   int fmt, float wscale, __nv_bfloat16* __restrict__ packed) {
   const int ntaps = ks * ks;
   const int kchunks = k_total / kBlockK;
   const long long rows = static_cast<long long>(n_total / nt) * ntaps * kchunks * 4 * nt;
@@ -75,11 +75,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
     const int k0 = kc * kBlockK + chunk * 8 + 2 * e;
     const float v0 = effective_weight(w, fir, cout, cin, ks, up, transpose, scale, n, tap, k0);
     const float v1 = effective_weight(w, fir, cout, cin, ks, up, transpose, scale, n, tap, k0 + 1);
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v0, h0, l0);
-    split_bf16(v1, h1, l1);
-    hi[e] = pack_bf16x2(h0, h1);
-    lo[e] = pack_bf16x2(l0, l1);
+    split2(v0 * wscale, v1 * wscale, fmt, hi[e], lo[e]);
   }
   const size_t slab = (static_cast<size_t>(ntile) * ntaps + tap) * kchunks + kc;        // stage index
   const size_t row_in_plane = static_cast<size_t>(chunk) * nt + nl;
@@ -180,7 +176,7 @@ __global__ void demod_kernel(const float* __restrict__ s, const float* __restric
 // NCHW fp32 (* scale[b,c]) -> C8 hi/lo planes.  One thread per (b, chunk, y, x) writes 16 B to each plane.
 // s2d: channel' = phase*C + c at (y/2, x/2), phase = (y&1)*2 + (x&1).
 __global__ void nchw_to_c8_kernel(const float* __restrict__ x, const float* __restrict__ scale, int batch, int C, int H,
-                                  int W, int s2d, __nv_bfloat16* __restrict__ out) {
+                                  int W, int s2d, int fmt, float ascale, __nv_bfloat16* __restrict__ out) {
   const long long total = static_cast<long long>(batch) * (C / 8) * H * W;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
@@ -200,11 +196,7 @@ __global__ void nchw_to_c8_kernel(const float* __restrict__ x, const float* __re
       if (scale) val *= __ldg(scale + static_cast<size_t>(b) * C + c);
       v[h] = val;
     }
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[0], h0, l0);
-    split_bf16(v[1], h1, l1);
-    hi[e] = pack_bf16x2(h0, h1);
-    lo[e] = pack_bf16x2(l0, l1);
+    split2(v[0] * ascale, v[1] * ascale, fmt, hi[e], lo[e]);
   }
   size_t off, plane;
   if (!s2d) {
@@ -223,7 +215,7 @@ __global__ void nchw_to_c8_kernel(const float* __restrict__ x, const float* __re
 
 // ConstantInput (model.py:290-300) times the first layer's style, straight into C8 planes.
 __global__ void const_input_kernel(const float* __restrict__ cinput, const float* __restrict__ s, int batch, int C,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   int fmt, float ascale, __nv_bfloat16* __restrict__ out) {
   const int total = batch * (C / 8) * 16;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -236,11 +228,7 @@ __global__ void const_input_kernel(const float* __restrict__ cinput, const float
     const int c = ch * 8 + 2 * e;
     const float v0 = __ldg(cinput + c * 16 + pix) * __ldg(s + static_cast<size_t>(b) * C + c);
     const float v1 = __ldg(cinput + (c + 1) * 16 + pix) * __ldg(s + static_cast<size_t>(b) * C + c + 1);
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v0, h0, l0);
-    split_bf16(v1, h1, l1);
-    hi[e] = pack_bf16x2(h0, h1);
-    lo[e] = pack_bf16x2(l0, l1);
+    split2(v0 * ascale, v1 * ascale, fmt, hi[e], lo[e]);
   }
   uint4* o4 = reinterpret_cast<uint4*>(out);
   o4[idx] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -248,7 +236,7 @@ __global__ void const_input_kernel(const float* __restrict__ cinput, const float
 }
 
 // ------------------------------------------------------------------------------------------------ host wrappers
-int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose,
+int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose, int fmt,
                        void* packed, float* wsq, cudaStream_t st) {
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
@@ -257,8 +245,8 @@ int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int 
   const long long rows = static_cast<long long>(n_total) * ks * ks * (k_total / 8);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((rows + threads - 1) / threads);
-  pack_weight_kernel<<<blocks, threads, 0, st>>>(w, fir, cout, cin, ks, up, transpose, n_total, k_total, nt, scale,
-                                                 static_cast<__nv_bfloat16*>(packed));
+  pack_weight_kernel<<<blocks, threads, 0, st>>>(w, fir, cout, cin, ks, up, transpose, n_total, k_total, nt, scale, fmt,
+                                                 w_scale(fmt), static_cast<__nv_bfloat16*>(packed));
   count_launch();
   if (!check_launch("pack_weight_kernel")) return 1;
   if (wsq) {
@@ -294,18 +282,18 @@ int demod_launch(const float* s, const float* wsq, int batch, int cin, int cout,
   return check_launch("demod_kernel") ? 0 : 1;
 }
 
-int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d,
+int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d, int fmt,
                       cudaStream_t st) {
   const long long total = static_cast<long long>(batch) * (C / 8) * H * W;
-  nchw_to_c8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, scale, batch, C, H, W, s2d,
-                                                                                static_cast<__nv_bfloat16*>(out));
+  nchw_to_c8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, scale, batch, C, H, W, s2d, fmt,
+                                                                                act_scale(fmt), static_cast<__nv_bfloat16*>(out));
   count_launch();
   return check_launch("nchw_to_c8_kernel") ? 0 : 1;
 }
 
-int const_input_launch(const float* cinput, const float* s, int batch, int C, void* out, cudaStream_t st) {
+int const_input_launch(const float* cinput, const float* s, int batch, int C, int fmt, void* out, cudaStream_t st) {
   const int total = batch * (C / 8) * 16;
-  const_input_kernel<<<(total + 127) / 128, 128, 0, st>>>(cinput, s, batch, C, static_cast<__nv_bfloat16*>(out));
+  const_input_kernel<<<(total + 127) / 128, 128, 0, st>>>(cinput, s, batch, C, fmt, act_scale(fmt), static_cast<__nv_bfloat16*>(out));
   count_launch();
   return check_launch("const_input_kernel") ? 0 : 1;
 }

@@ -156,27 +156,29 @@ size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpo
 }
 
 int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up, int transpose,
-                            void* packed, float* wsq, void* stream) {
+                            int format, void* packed, float* wsq, void* stream) {
   if (!have_device()) return 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
   if (!weight || !packed || (up && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
-      k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0) {
+      k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0 ||
+      (format != SGR_FMT_BF16 && format != SGR_FMT_FP16)) {
     set_error("pack_modconv_weight: unsupported cout=%d cin=%d k=%d up=%d transpose=%d", cout, cin, ksize, up,
               transpose);
     return 1;
   }
-  return pack_weight_launch(weight, fir, cout, cin, ksize, up, transpose, packed, wsq, static_cast<cudaStream_t>(stream));
+  return pack_weight_launch(weight, fir, cout, cin, ksize, up, transpose, format, packed, wsq,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, int channels, int h, int w, int s2d,
-                   void* stream) {
+                   int format, void* stream) {
   if (!have_device()) return 1;
   if (!x || !out_c8 || channels % 8 != 0 || (s2d && ((h | w) & 1))) {
     set_error("nchw_to_c8: bad arguments (C=%d H=%d W=%d)", channels, h, w);
     return 1;
   }
-  return nchw_to_c8_launch(x, scale, out_c8, batch, channels, h, w, s2d, static_cast<cudaStream_t>(stream));
+  return nchw_to_c8_launch(x, scale, out_c8, batch, channels, h, w, s2d, format, static_cast<cudaStream_t>(stream));
 }
 
 int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
@@ -293,7 +295,8 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     return 1;
   }
   int cur = 0;
-  if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, net->styled[0].cin, ws + pl.act_off[cur], st))
+  if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, net->styled[0].cin, net->format,
+                         ws + pl.act_off[cur], st))
     return 1;
 
   // 4. the layer chain
@@ -314,6 +317,8 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     a.up = L.up;
     a.act = 1;
     a.act_gain = 1.4142135623730951f;
+    a.operand_format = net->format;
+    a.out_format = net->format;
     a.x_c8 = ws + pl.act_off[cur];
     a.w_packed = L.w_packed;
     a.demod = F(pl.demod_off[l]);

@@ -14,6 +14,13 @@ constexpr int kTileM = 128;      // GEMM rows (pixels) per CTA tile == TMEM lane
 constexpr int kBlockK = 32;      // input channels per pipeline stage (4 chunks of 8)
 constexpr int kABytes = 2 * kTileM * kBlockK * 2;   // hi+lo planes of one A stage = 16 KiB
 
+// Static scales of the fp16 operand format (SGR_FMT_FP16): activations are stored x 2^-4 (range 1e6, absolute
+// resolution 5e-7), weights x 2^8 (keeps the lo halves of 1/sqrt(fan_in)-sized weights out of the fp16 subnormals).
+constexpr float kActScaleFP16 = 0.0625f;
+constexpr float kWScaleFP16 = 256.f;
+inline float act_scale(int fmt) { return fmt == SGR_FMT_FP16 ? kActScaleFP16 : 1.f; }
+inline float w_scale(int fmt) { return fmt == SGR_FMT_FP16 ? kWScaleFP16 : 1.f; }
+
 // GEMM column tile for a layer with n_total columns.
 inline int pick_nt(int n_total) { return n_total >= 256 ? 256 : n_total; }
 
@@ -33,6 +40,10 @@ struct ConvKernelParams {
   int Hout, Wout;
   int act;
   float act_gain;
+  int fmt;                      // operand format of x_c8 / wpacked (SGR_FMT_*)
+  float acc_scale;              // undoes the operand scales on the accumulator
+  int out_fmt;                  // format of out_c8
+  float out_scale;              // activation scale of out_fmt
   const __nv_bfloat16* wpacked;
   const float* demod;
   const float* bias;
@@ -80,14 +91,14 @@ struct TableJobs {
   TableJob job[SGR_MAX_STYLED];
   int n;
 };
-int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose,
+int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose, int fmt,
                        void* packed, float* wsq, cudaStream_t st);
 int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st);
 int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st);
 int demod_launch(const float* s, const float* wsq, int batch, int cin, int cout, float* d, cudaStream_t st);
-int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d,
+int nchw_to_c8_launch(const float* x, const float* scale, void* out, int batch, int C, int H, int W, int s2d, int fmt,
                       cudaStream_t st);
-int const_input_launch(const float* cinput, const float* s, int batch, int C, void* out, cudaStream_t st);
+int const_input_launch(const float* cinput, const float* s, int batch, int C, int fmt, void* out, cudaStream_t st);
 // upfirdn2d_sm100.cu
 int upfirdn2d_launch(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int up, int down,
                      int pad0, int pad1, int kh, int kw, cudaStream_t st);

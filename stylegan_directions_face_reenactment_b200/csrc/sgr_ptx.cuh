@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -130,6 +131,36 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+// Operand formats of the split-precision GEMM (both use kind::f16 MMAs, 3 per product):
+//   kFmtBF16: bf16 hi/lo, 16 mantissa bits, fp32 range              -> ~2e-5 relative, used for gradients
+//   kFmtFP16: fp16 hi/lo, 22 mantissa bits, values pre-scaled by the caller into fp16 range and SATURATED at
+//             +-65504 instead of overflowing                        -> ~5e-7 relative, used for the forward pass
+constexpr int kFmtBF16 = 0;
+constexpr int kFmtFP16 = 1;
+
+// Split two fp32 values; returns the packed hi pair and lo pair (16-bit patterns of the chosen format).
+__device__ __forceinline__ void split2(float v0, float v1, int fmt, uint32_t& hi, uint32_t& lo) {
+  if (fmt == kFmtBF16) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    hi = pack_bf16x2(h0, h1);
+    lo = pack_bf16x2(l0, l1);
+  } else {
+    v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
+    v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+    const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+    hi = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+    lo = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+  }
+}
+// Instruction descriptor for either operand format (F16 = 0, BF16 = 1 in bits [7,10) and [10,13)).
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int m, int n) {
+  return (1u << 4) | ((fmt == kFmtBF16 ? 1u : 0u) << 7) | ((fmt == kFmtBF16 ? 1u : 0u) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace sgr

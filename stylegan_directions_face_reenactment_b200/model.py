@@ -152,11 +152,13 @@ class ModulatedConv2d(nn.Module):
             new.__dict__[k] = {} if k == '_pack_cache' else copy.deepcopy(v, memo)
         return new
 
-    def packed(self, transpose=False):
-        """(w_packed, wsq) device tensors for the tcgen05 kernel; repacked when the parameter changes."""
+    def packed(self, transpose=False, fmt=None):
+        """(w_packed, wsq) device tensors for the tcgen05 kernel; repacked when the parameter changes.
+        The adjoint (transpose) is always packed as bf16 hi/lo: it multiplies gradients (csrc/backward.cu)."""
         w = self.weight
         fir = self.blur.kernel if self.upsample else None
-        key = ('T' if transpose else 'N',) + _version_key(*([w] + ([fir] if fir is not None else [])))
+        fmt = N.FMT_BF16 if transpose else (N.default_format() if fmt is None else fmt)
+        key = ('T' if transpose else 'N', fmt) + _version_key(*([w] + ([fir] if fir is not None else [])))
         hit = self._pack_cache.get(bool(transpose))
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
@@ -178,7 +180,7 @@ class ModulatedConv2d(nn.Module):
         wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if not transpose else None
         firc = None if fir is None else fir.detach().contiguous().float()
         N.check(lib.sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, int(self.upsample), int(transpose),
-                                            N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
+                                            fmt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
         self._pack_cache[bool(transpose)] = (key, packed, wsq)
         return packed, wsq
 
@@ -201,7 +203,8 @@ def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
     s = torch.empty(b, cin, device=dev)
     N.check(lib.sgr_style_affine(N.ptr(style), style.shape[1], b, N.ptr(mw), N.ptr(mb), cin, N.ptr(s), st),
             'sgr_style_affine')
-    packed, wsq = conv.packed()
+    fmt = N.default_format()
+    packed, wsq = conv.packed(fmt=fmt)
     cout_k = wsq.shape[0]
     if wsq.shape[1] != cin:                                  # channel padding (see packed())
         padc = wsq.shape[1] - cin
@@ -213,13 +216,14 @@ def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
         d = torch.empty(b, cout_k, device=dev)
         N.check(lib.sgr_demod(N.ptr(s), N.ptr(wsq), b, cin, cout_k, N.ptr(d), st), 'sgr_demod')
     xc8 = torch.empty(2 * b * cin * h * w, dtype=torch.bfloat16, device=dev)
-    N.check(lib.sgr_nchw_to_c8(N.ptr(x), N.ptr(s), N.ptr(xc8), b, cin, h, w, 0, st), 'sgr_nchw_to_c8')
+    N.check(lib.sgr_nchw_to_c8(N.ptr(x), N.ptr(s), N.ptr(xc8), b, cin, h, w, 0, fmt, st), 'sgr_nchw_to_c8')
     ho, wo = (2 * h, 2 * w) if conv.upsample else (h, w)
     out = torch.empty(b, cout_k, ho, wo, device=dev)
     a = N.ConvArgs()
     a.batch, a.cin, a.cout, a.h_in, a.w_in = b, cin, cout_k, h, w
     a.ksize, a.up, a.act = conv.kernel_size, int(conv.upsample), int(act)
     a.act_gain = SQRT2 if act else 1.0
+    a.operand_format = a.out_format = fmt
     a.x_c8, a.w_packed, a.demod = N.ptr(xc8), N.ptr(packed), N.ptr(d)
     if bias is not None:
         bias = bias.detach().contiguous().float()

@@ -25,10 +25,11 @@ class NetDescriptor:
         styled = g.styled_layers()
         rgbs = g.rgb_layers()
         s.size, s.n_styled, s.n_rgb, s.n_latent = g.size, len(styled), len(rgbs), g.n_latent
+        s.format = N.default_format()
         s.const_input = self._p(g.input.input)
         for l, layer in enumerate(styled):
             conv = layer.conv
-            packed, wsq = conv.packed()
+            packed, wsq = conv.packed(fmt=s.format)
             d = s.styled[l]
             d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, int(conv.upsample)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
