@@ -13,8 +13,10 @@ FMT_BF16, FMT_FP16 = 0, 1
 
 
 def default_format():
-    """Forward operand format: fp16 hi/lo split (default) or bf16 hi/lo via SGR_PRECISION=bf16x3 (csrc/sgr_ptx.cuh)."""
-    v = os.environ.get('SGR_PRECISION', 'fp16x3').lower()
+    """Forward operand format: bf16 hi/lo split (default, fp32 range) or fp16 hi/lo via SGR_PRECISION=fp16x3
+    (22-bit operands, statically scaled, saturating; csrc/sgr_ptx.cuh).  Measured on B200 the two agree to within the
+    tensor core's fp32-accumulate rounding for K >= 2304, so the range-safe format is the default."""
+    v = os.environ.get('SGR_PRECISION', 'bf16x3').lower()
     if v not in ('fp16x3', 'bf16x3'):
         raise RuntimeError('SGR_PRECISION must be fp16x3 or bf16x3, got %r' % v)
     return FMT_FP16 if v == 'fp16x3' else FMT_BF16
