@@ -75,8 +75,12 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
  * wsq:    [cout, cin] fp32 = sum_k (weight*scale)^2 for the demodulation mini-GEMM (may be NULL).
  */
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose);
+/* GEMM column tile (32/64/128/256) the library would pick for a layer with n_total GEMM columns (cout, x4 for up
+ * layers; cin for the adjoint) on an h_in x w_in grid at this batch: fills the 148 SMs on the small layers.  The packed
+ * weight layout depends on it, so pack and convolve with the same value (0 = the default min(n_total, 256)). */
+int sgr_choose_column_tile(int batch, int h_in, int w_in, int n_total);
 int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up,
-                            int transpose, int format, void* packed, float* wsq, void* stream);
+                            int transpose, int format, int column_tile, void* packed, float* wsq, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Layout helpers (module-level calls and tests; the fused network path never needs them).
@@ -103,6 +107,7 @@ typedef struct sgr_conv_args {
   int act;                /* apply leaky-relu 0.2 */
   float act_gain;         /* sqrt(2) for StyledConv, 1 for raw conv */
   int operand_format;     /* SGR_FMT_* of x_c8 and w_packed */
+  int column_tile;        /* the value w_packed was packed with (0 = default) */
   int out_format;         /* SGR_FMT_* written to out_c8 */
   const void* x_c8;       /* [2][B][cin/8][h_in][w_in][8] bf16 */
   const void* w_packed;
@@ -130,6 +135,8 @@ int sgr_demod(const float* s, const float* wsq, int batch, int cin, int cout, fl
  */
 typedef struct sgr_styled_layer {
   int cin, cout, up, latent_row;
+  int column_tile;           /* of w_packed (0 = default) */
+  int column_tile_t;         /* of w_packed_t */
   const void* w_packed;      /* forward operator, sgr_pack_modconv_weight(transpose=0) */
   const void* w_packed_t;    /* adjoint operator (transpose=1); only sgr_synthesis_backward reads it, may be NULL otherwise */
   const float* wsq;          /* [cout,cin] */

@@ -405,6 +405,7 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     a.act_gain = 1.f;
     a.operand_format = SGR_FMT_BF16;      // gradients have no a-priori range: bf16 split (fp32 exponent)
     a.out_format = SGR_FMT_BF16;
+    a.column_tile = Ly.column_tile_t;
     a.x_c8 = ws + pl.gz_off;
     a.w_packed = Ly.w_packed_t;
     a.out_f32 = F(pl.gx_off[gx_cur]);

@@ -21,6 +21,7 @@
 // warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/style/ToRGB -> HBM).
 // The accumulator is double-buffered in TMEM (2 x NT columns) so the epilogue of tile t overlaps the MMAs of t+1.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "sgr_internal.h"
 #include "sgr_ptx.cuh"
@@ -359,10 +360,37 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-static int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
+
+void tile_box(int h, int w, int* bw, int* bh, int* bb) {
+  int pw = 1, ph = 1;
+  while (pw < w) pw <<= 1;
+  while (ph < h) ph <<= 1;
+  *bw = std::min(pw, 16);
+  *bh = std::min(ph, kTileM / *bw);
+  *bb = kTileM / (*bw * *bh);
+}
+
+// Column tile minimising rounds x per-tile MMA time (cycles per K=16 step: 128/64/48/40 for N=256/128/64/32; the two
+// small ones are bound by the shared-memory read of the 128-row A operand, not by the MMA; 80/52 are calibrated).
+int choose_nt(int batch, int h, int w, int n_total) {
+  int bw, bh, bb;
+  tile_box(h, w, &bw, &bh, &bb);
+  const long long m_tiles = static_cast<long long>((w + bw - 1) / bw) * ((h + bh - 1) / bh) * ((batch + bb - 1) / bb);
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  int best = pick_nt(n_total);
+  double best_cost = 1e300;
+  for (int nt = 256; nt >= 64; nt >>= 1) {
+    if (nt > n_total || n_total % nt) continue;
+    const double per_tile = nt == 256 ? 128 : nt == 128 ? 80 : 52;   // measured: N<=128 is operand-read bound
+    const long long tiles = m_tiles * (n_total / nt);
+    const double cost = static_cast<double>((tiles + sms - 1) / sms) * per_tile;
+    if (cost < best_cost * 0.95) {       // prefer the larger tile unless clearly better
+      best_cost = cost;
+      best = nt;
+    }
+  }
+  return best;
 }
 
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
@@ -394,15 +422,17 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->B = a->batch;
   p->H = a->h_in;
   p->W = a->w_in;
-  p->bw = std::min(next_pow2(a->w_in), 16);
-  p->bh = std::min(next_pow2(a->h_in), kTileM / p->bw);
-  p->bb = kTileM / (p->bw * p->bh);
+  tile_box(a->h_in, a->w_in, &p->bw, &p->bh, &p->bb);
   p->tiles_x = (a->w_in + p->bw - 1) / p->bw;
   p->tiles_y = (a->h_in + p->bh - 1) / p->bh;
   p->tiles_b = (a->batch + p->bb - 1) / p->bb;
   p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
   const int n_total = a->cout * (a->up ? 4 : 1);
-  *nt = pick_nt(n_total);
+  *nt = a->column_tile > 0 ? a->column_tile : pick_nt(n_total);
+  if (*nt > n_total || n_total % *nt != 0 || (*nt != 32 && *nt != 64 && *nt != 128 && *nt != 256)) {
+    set_error("modconv: column tile %d does not fit %d columns", *nt, n_total);
+    return 1;
+  }
   p->n_tiles = n_total / *nt;
   p->kchunks = a->cin / kBlockK;
   p->ntaps = a->ksize * a->ksize;
@@ -419,6 +449,10 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   }
   p->fmt = a->operand_format;
   p->acc_scale = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
+  // The tensor core's fp32 accumulate truncates: measured on B200 the result shrinks by ~1.16e-8 per MMA accumulated into
+  // the same TMEM cell (tools/gpu_debug.py "mean signed rel err": -1.0e-5 at 864 MMAs, -1.6e-6 at 108).  Undo the mean.
+  static const bool comp = [] { const char* e = getenv("SGR_ACC_COMP"); return !(e && e[0] == '0'); }();
+  if (comp) p->acc_scale *= 1.f + 1.16e-8f * static_cast<float>(3 * a->ksize * a->ksize * (a->cin / 16));
   p->out_fmt = a->out_format;
   p->out_scale = act_scale(a->out_format);
   p->wpacked = static_cast<const __nv_bfloat16*>(a->w_packed);

@@ -237,10 +237,10 @@ __global__ void const_input_kernel(const float* __restrict__ cinput, const float
 
 // ------------------------------------------------------------------------------------------------ host wrappers
 int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose, int fmt,
-                       void* packed, float* wsq, cudaStream_t st) {
+                       int nt_req, void* packed, float* wsq, cudaStream_t st) {
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
-  const int nt = pick_nt(n_total);
+  const int nt = nt_req > 0 ? nt_req : pick_nt(n_total);
   const float scale = 1.f / sqrtf(static_cast<float>(cin) * ks * ks);
   const long long rows = static_cast<long long>(n_total) * ks * ks * (k_total / 8);
   const int threads = 256;

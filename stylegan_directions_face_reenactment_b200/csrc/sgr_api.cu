@@ -149,6 +149,11 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
   return bias_act_launch(x, bias, ref, y, outer, channels, inner, grad, slope, scale, static_cast<cudaStream_t>(stream));
 }
 
+int sgr_choose_column_tile(int batch, int h_in, int w_in, int n_total) {
+  if (batch <= 0 || h_in <= 0 || w_in <= 0 || n_total < 32) return 0;
+  return choose_nt(batch, h_in, w_in, n_total);
+}
+
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose) {
   const size_t n_total = transpose ? cin : static_cast<size_t>(cout) * (up ? 4 : 1);
   const size_t k_total = transpose ? static_cast<size_t>(cout) * (up ? 4 : 1) : cin;
@@ -156,18 +161,20 @@ size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpo
 }
 
 int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up, int transpose,
-                            int format, void* packed, float* wsq, void* stream) {
+                            int format, int column_tile, void* packed, float* wsq, void* stream) {
   if (!have_device()) return 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
   if (!weight || !packed || (up && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
       k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0 ||
-      (format != SGR_FMT_BF16 && format != SGR_FMT_FP16)) {
+      (format != SGR_FMT_BF16 && format != SGR_FMT_FP16) ||
+      (column_tile != 0 && (column_tile > n_total || n_total % column_tile != 0 ||
+                            (column_tile != 32 && column_tile != 64 && column_tile != 128 && column_tile != 256)))) {
     set_error("pack_modconv_weight: unsupported cout=%d cin=%d k=%d up=%d transpose=%d", cout, cin, ksize, up,
               transpose);
     return 1;
   }
-  return pack_weight_launch(weight, fir, cout, cin, ksize, up, transpose, format, packed, wsq,
+  return pack_weight_launch(weight, fir, cout, cin, ksize, up, transpose, format, column_tile, packed, wsq,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -318,6 +325,7 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     a.act = 1;
     a.act_gain = 1.4142135623730951f;
     a.operand_format = net->format;
+    a.column_tile = L.column_tile;
     a.out_format = net->format;
     a.x_c8 = ws + pl.act_off[cur];
     a.w_packed = L.w_packed;

@@ -23,6 +23,8 @@ inline float w_scale(int fmt) { return fmt == SGR_FMT_FP16 ? kWScaleFP16 : 1.f; 
 
 // GEMM column tile for a layer with n_total columns.
 inline int pick_nt(int n_total) { return n_total >= 256 ? 256 : n_total; }
+int choose_nt(int batch, int h, int w, int n_total);
+void tile_box(int h, int w, int* bw, int* bh, int* bb);
 
 void set_error(const char* fmt, ...);
 void count_launch();
@@ -92,7 +94,7 @@ struct TableJobs {
   int n;
 };
 int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose, int fmt,
-                       void* packed, float* wsq, cudaStream_t st);
+                       int nt, void* packed, float* wsq, cudaStream_t st);
 int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st);
 int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st);
 int demod_launch(const float* s, const float* wsq, int batch, int cin, int cout, float* d, cudaStream_t st);

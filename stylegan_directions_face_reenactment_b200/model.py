@@ -152,23 +152,26 @@ class ModulatedConv2d(nn.Module):
             new.__dict__[k] = {} if k == '_pack_cache' else copy.deepcopy(v, memo)
         return new
 
-    def packed(self, transpose=False, fmt=None):
+    def packed(self, transpose=False, fmt=None, nt=0):
         """(w_packed, wsq) device tensors for the tcgen05 kernel; repacked when the parameter changes.
-        The adjoint (transpose) is always packed as bf16 hi/lo: it multiplies gradients (csrc/backward.cu)."""
+        The adjoint (transpose) is always packed as bf16 hi/lo: it multiplies gradients (csrc/backward.cu).
+        `nt` is the GEMM column tile the layout is built for (0 = library default, see sgr_choose_column_tile)."""
         w = self.weight
         fir = self.blur.kernel if self.upsample else None
         fmt = N.FMT_BF16 if transpose else (N.default_format() if fmt is None else fmt)
-        key = ('T' if transpose else 'N', fmt) + _version_key(*([w] + ([fir] if fir is not None else [])))
-        hit = self._pack_cache.get(bool(transpose))
-        if hit is not None and hit[0] == key:
-            return hit[1], hit[2]
+        version = _version_key(*([w] + ([fir] if fir is not None else [])))
+        if self._pack_cache.get('version') != version:          # parameter changed: every packed variant is stale
+            self._pack_cache.clear()
+            self._pack_cache['version'] = version
+        slot = (bool(transpose), fmt, nt)
+        hit = self._pack_cache.get(slot)
+        if hit is not None:
+            return hit
         cout, cin, ks = self.out_channel, self.in_channel, self.kernel_size
         wd = w.detach()
-        pad_to = None
         if not transpose and cout < 32:                      # ToRGB (3 channels): pad the GEMM columns to 32
-            pad_to = 32
-            wd = torch.cat([wd[0], wd.new_zeros(pad_to - cout, cin, ks, ks)], 0)
-            cout = pad_to
+            wd = torch.cat([wd[0], wd.new_zeros(32 - cout, cin, ks, ks)], 0)
+            cout = 32
         wd = wd.reshape(cout, cin, ks, ks)
         if cin % 32:                                         # zero input channels up to the K granularity
             wd = torch.cat([wd, wd.new_zeros(cout, 32 - cin % 32, ks, ks)], 1) * math.sqrt((cin + 32 - cin % 32) / cin)
@@ -180,8 +183,8 @@ class ModulatedConv2d(nn.Module):
         wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if not transpose else None
         firc = None if fir is None else fir.detach().contiguous().float()
         N.check(lib.sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, int(self.upsample), int(transpose),
-                                            fmt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
-        self._pack_cache[bool(transpose)] = (key, packed, wsq)
+                                            fmt, nt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
+        self._pack_cache[slot] = (packed, wsq)
         return packed, wsq
 
     def forward(self, input, style):

@@ -29,13 +29,18 @@ class NetDescriptor:
         s.const_input = self._p(g.input.input)
         for l, layer in enumerate(styled):
             conv = layer.conv
-            packed, wsq = conv.packed(fmt=s.format)
             d = s.styled[l]
             d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, int(conv.upsample)
+            res_out = 4 << ((l + 1) // 2)
+            res_in = res_out // 2 if conv.upsample else res_out
+            n_fwd = conv.out_channel * (4 if conv.upsample else 1)
+            d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, n_fwd)
+            packed, wsq = conv.packed(fmt=s.format, nt=d.column_tile)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
             d.w_packed, d.wsq = self._p(packed), self._p(wsq)
             if backward:
-                d.w_packed_t = self._p(conv.packed(transpose=True)[0])
+                d.column_tile_t = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.in_channel)
+                d.w_packed_t = self._p(conv.packed(transpose=True, nt=d.column_tile_t)[0])
             d.mod_weight, d.mod_bias = self._p(conv.modulation.weight), self._p(conv.modulation.bias)
             nz = noise[l]
             res = 4 << ((l + 1) // 2)

@@ -314,3 +314,45 @@ def test_backward_with_randomized_noise_is_consistent(pkg):
     img, _ = G([w], input_is_latent=True, randomize_noise=True)
     img.square().mean().backward()
     assert torch.isfinite(w.grad).all() and w.grad.abs().max() > 0
+
+
+# ------------------------------------------------------------------------------------------ other BASELINE configs
+@pytest.mark.parametrize('size,cm,batch', [(256, 2, 2), (1024, 2, 1)])
+def test_generator_ffhq_configs_vs_oracle(pkg, size, cm, batch):
+    """ffhq-256 (cm=2) and the 1024^2 network of BASELINE config 5 (fp32-parity mode), forward vs the CPU oracle."""
+    sd = orc.seeded_state_dict(size, cm, seed=5)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, batch, G.n_latent, seed=17)
+    with torch.no_grad():
+        img = G([wplus.cuda()], input_is_latent=True)[0]
+        ref, _ = orc.generator_forward(sd, [wplus], size, cm, input_is_latent=True)
+        assert err(img, ref.numpy()) <= 1e-3
+        if size > 256:                                            # generate_image pools 1024^2 to 256^2 (generic.py:146-148)
+            pooled = pkg.generate_image(G, wplus.cuda(), 1.0, None, input_is_latent=True)
+            assert tuple(pooled.shape) == (batch, 3, 256, 256)
+
+
+def test_train_step_config4_shapes(pkg):
+    """BASELINE config 4 in miniature: A-matrix step (2 no-grad forwards from Z + 1 autograd forward + backward to A)."""
+    from stylegan_directions_face_reenactment_b200 import dist as sdist
+    size, cm, batch = 64, 1, 4
+    sd = orc.seeded_state_dict(size, cm, seed=6)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    torch.manual_seed(0)
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=8).cuda()
+    opt = torch.optim.Adam(A.parameters(), lr=1e-4, weight_decay=5e-4)
+    trunc = G.mean_latent(256).detach()
+    z_src, z_tgt = torch.randn(batch, 512, device='cuda'), torch.randn(batch, 512, device='cuda')
+    with torch.no_grad():
+        src, w_src = pkg.generate_image(G, z_src, 0.7, trunc, input_is_latent=False, return_latents=True)
+        tgt = pkg.generate_image(G, z_tgt, 0.7, trunc, input_is_latent=False)
+    dp = torch.rand(batch, 15, device='cuda') * 6 - 3
+    before = A.linear.weight.detach().clone()
+    # generate_image re-applies the truncation to the (already truncated) W+ code, exactly like libs/trainer.py:177
+    loss, nbytes = sdist.train_step(G, A, opt, w_src, dp, 0.7, trunc, lambda img: (img - tgt).abs().mean())
+    assert torch.isfinite(loss) and nbytes == 0 and not torch.equal(before, A.linear.weight)
+    assert tuple(src.shape) == (batch, 3, size, size)
