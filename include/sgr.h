@@ -68,13 +68,18 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
 /* ---------------------------------------------------------------------------------------------------------
  * Weight packing for the tcgen05 implicit-GEMM convolution.
  * weight: [cout, cin, k, k] fp32 (the reference parameter ModulatedConv2d.weight[0], model.py:216-218), k = 3 or 1.
- * up != 0: the stride-2 transposed conv + 4x4 FIR of model.py:246-257 is folded into four 3x3 phase kernels
- *          (W (*) fir, 6x6); fir = the layer's blur.kernel buffer [4,4].
+ * up == 1: the stride-2 transposed conv + 4x4 FIR of model.py:246-257 is folded into four 3x3 phase kernels
+ *          (W (*) fir, 6x6); fir = the layer's blur.kernel buffer [4,4].  36 Cin Cout MACs / input pixel.
+ * up == 2: scatter form at the minimal 9 Cin Cout MACs / input pixel: the 9 taps are packed by (row,column) shift of
+ *          the input tile and output parity; the FIR runs afterwards on the parity planes (sgr_modconv_forward does
+ *          both).  fir is not needed for packing.  Fixed column tile: 256 (cout >= 64) or 4*cout.
  * transpose != 0 packs the adjoint (data-gradient) operator instead: GEMM columns = cin, K = cout (x4 for up).
  * packed: bf16 hi/lo slabs in shared-memory image order, sgr_packed_weight_bytes() bytes.
  * wsq:    [cout, cin] fp32 = sum_k (weight*scale)^2 for the demodulation mini-GEMM (may be NULL).
  */
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose);
+/* bytes of the fp32 parity-plane scratch an up == 2 convolution needs: [B][4][cout/8][h_in+1][w_in+1][8] */
+size_t sgr_up_scratch_bytes(int batch, int cout, int h_in, int w_in);
 /* GEMM column tile (32/64/128/256) the library would pick for a layer with n_total GEMM columns (cout, x4 for up
  * layers; cin for the adjoint) on an h_in x w_in grid at this batch: fills the 148 SMs on the small layers.  The packed
  * weight layout depends on it, so pack and convolve with the same value (0 = the default min(n_total, 256)). */
@@ -98,12 +103,15 @@ int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, 
  *   t   = act ? max(t, 0.2 t) : t
  *   out_f32[b,o,y,x]  = t * act_gain                                  (optional, NCHW fp32)
  *   out_c8            = split_bf16(t * (s2 ? s2[b,o] : act_gain))     (optional, next layer's input)
- *   rgb_acc[b,c,y,x] += sum_o t * rgb_coef[b,c,o]                     (optional fused ToRGB, atomic)
+ *   rgb_partial[n_tile][b,c,y,x] = sum_{o in column tile} t * rgb_coef[b,c,o]   (optional fused ToRGB; one slot per
+ *                                    column tile, plain stores: summing the slots in order is deterministic)
+ * up == 2 runs two kernels: the tensor-core GEMM leaves the four parity planes of conv_transpose2d in t_scratch, then
+ * an HBM-bound kernel applies the 4x4 FIR (Blur, model.py:72-88) and the same fused epilogue.
  */
 typedef struct sgr_conv_args {
   int batch, cin, cout, h_in, w_in;
   int ksize;              /* 3 or 1 */
-  int up;                 /* 0: same resolution; 1: output is 2x (polyphase), cout phases packed by sgr_pack_modconv_weight */
+  int up;                 /* 0: same resolution; 1: output is 2x, polyphase weights; 2: output is 2x, scatter weights + FIR pass */
   int act;                /* apply leaky-relu 0.2 */
   float act_gain;         /* sqrt(2) for StyledConv, 1 for raw conv */
   int operand_format;     /* SGR_FMT_* of x_c8 and w_packed */
@@ -120,7 +128,9 @@ typedef struct sgr_conv_args {
   void* out_c8;           /* or NULL */
   float* out_f32;         /* or NULL */
   const float* rgb_coef;  /* [B,3,cout] or NULL */
-  float* rgb_acc;         /* [B,3,h_out,w_out], must be zero-initialised by the caller */
+  float* rgb_partial;     /* [cout/column_tile][B,3,h_out,w_out], fully overwritten */
+  float* t_scratch;       /* up == 2: sgr_up_scratch_bytes() of scratch */
+  const float* fir;       /* up == 2: blur.kernel [4,4] */
 } sgr_conv_args;
 int sgr_modconv_forward(const sgr_conv_args* args, void* stream);
 
@@ -134,7 +144,9 @@ int sgr_demod(const float* s, const float* wsq, int batch, int cin, int cout, fl
  * Whole synthesis network (Generator.forward after the mapping/truncation glue, model.py:519-534).
  */
 typedef struct sgr_styled_layer {
-  int cin, cout, up, latent_row;
+  int cin, cout;
+  int up;                    /* 0, or the packing mode of w_packed for an upsampling layer: 1 polyphase, 2 scatter */
+  int latent_row;
   int column_tile;           /* of w_packed (0 = default) */
   int column_tile_t;         /* of w_packed_t */
   const void* w_packed;      /* forward operator, sgr_pack_modconv_weight(transpose=0) */
@@ -146,6 +158,7 @@ typedef struct sgr_styled_layer {
   long long noise_batch_stride;
   const float* noise_weight; /* [1] */
   const float* act_bias;     /* [cout] */
+  const float* fir;          /* blur.kernel [4,4] of an upsampling layer (read when up == 2) */
 } sgr_styled_layer;
 
 typedef struct sgr_rgb_layer {

@@ -29,13 +29,13 @@ class ConvArgs(C.Structure):
                 ('ksize', C.c_int), ('up', C.c_int), ('act', C.c_int), ('act_gain', C.c_float), ('operand_format', C.c_int), ('column_tile', C.c_int), ('out_format', C.c_int),
                 ('x_c8', _fp), ('w_packed', _fp), ('demod', _fp), ('bias', _fp), ('noise', _fp),
                 ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('s2', _fp), ('out_c8', _fp),
-                ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_acc', _fp)]
+                ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_partial', _fp), ('t_scratch', _fp), ('fir', _fp)]
 
 
 class StyledLayer(C.Structure):
     _fields_ = [('cin', C.c_int), ('cout', C.c_int), ('up', C.c_int), ('latent_row', C.c_int),
                 ('column_tile', C.c_int), ('column_tile_t', C.c_int), ('w_packed', _fp), ('w_packed_t', _fp), ('wsq', _fp), ('mod_weight', _fp), ('mod_bias', _fp), ('noise', _fp),
-                ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('act_bias', _fp)]
+                ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('act_bias', _fp), ('fir', _fp)]
 
 
 class RgbLayer(C.Structure):
@@ -60,6 +60,7 @@ SIGNATURES = {
     'sgr_fused_bias_act': (C.c_int, [_fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                      C.c_float, _fp]),
     'sgr_packed_weight_bytes': (C.c_size_t, [C.c_int] * 5),
+    'sgr_up_scratch_bytes': (C.c_size_t, [C.c_int] * 4),
     'sgr_pack_modconv_weight': (C.c_int, [_fp, _fp] + [C.c_int] * 7 + [_fp, _fp, _fp]),
     'sgr_choose_column_tile': (C.c_int, [C.c_int] * 4),
     'sgr_nchw_to_c8': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 6 + [_fp]),

@@ -385,7 +385,7 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     p.noise_bstride = Ly.noise_batch_stride;
     p.noise_w = Ly.noise_weight;
     p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
-    p.s2d = Ly.up;
+    p.s2d = Ly.up ? 1 : 0;
     p.act = 1;
     p.ds_next = gx_next ? F(pl.ds_off[l + 1]) : nullptr;
     p.q = F(pl.q_off[l]);

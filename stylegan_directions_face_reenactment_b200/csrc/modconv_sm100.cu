@@ -17,10 +17,19 @@
 // Shared-memory operand layout (no swizzle, K-major): [plane][chunk of 8 channels][row][8 bf16]; a row is 16 B,
 // rows are contiguous (SBO = 128 B per 8 rows), K chunks are LBO = rows*16 B apart.
 //
+// Upsampling layers, scatter mode (p.mode == 2): conv_transpose2d(stride 2) at its MINIMAL flop count.  The (2H+1)^2
+// intermediate t[2i+ky, 2j+kx] += x[i,j] W[ky,kx] splits into four parity planes on the (H+1)x(W+1) grid
+//   ee[I,J] = sum_{a,b} x[I-a,J-b] W[2a,2b]   eo[I,J] = sum_a x[I-a,J] W[2a,1]
+//   oe[I,J] = sum_b x[I,J-b] W[1,2b]          oo[I,J] = x[I,J] W[1,1]
+// i.e. four shifted A tiles (shift = (a,b)) times column blocks [oe|ee|eo|oo] of the accumulator: shift (0,0) feeds all
+// four blocks (N = NT), (0,1) feeds [oe|ee], (1,0) feeds [ee|eo], (1,1) feeds [ee]: 9 Cin Cout MACs per input pixel.  The
+// raw planes go to HBM (fp32) and up_finish_kernel applies the 4x4 FIR + the fused epilogue.
+//
 // Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
 // warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/style/ToRGB -> HBM).
 // The accumulator is double-buffered in TMEM (2 x NT columns) so the epilogue of tile t overlaps the MMAs of t+1.
 #include <algorithm>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "sgr_internal.h"
@@ -99,19 +108,42 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int x0 = tc.tx * p.bw, y0 = tc.ty * p.bh, b0 = tc.tb * p.bb;
-        const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const uint32_t s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa = stage_base + s * Cfg::kStageBytes;
-            mbar_expect_tx(&full[s], Cfg::kStageBytes);
-            tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
-            bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(tap * p.kchunks + kc) * (NT * 64), Cfg::kBBytes,
-                     &full[s]);
+        const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
+        if (p.mode == 2) {
+          // scatter up-conv: 4 shifted activation tiles, weight slabs of NT, NT/2, NT/2, NT/4 rows
+          const uint8_t* wtile = reinterpret_cast<const uint8_t*>(p.wpacked) +
+                                 static_cast<size_t>(tc.n_tile) * p.kchunks * (NT / 4 * 9) * 128;
+          // k order: channel block outer, shift inner -> the four shifted boxes of a block hit the same L2 lines and the
+          // weight slabs [n_tile][kc][shift] stream linearly
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            const uint8_t* wkc = wtile + static_cast<size_t>(kc) * (NT / 4 * 9) * 128;
+            for (int sft = 0; sft < 4; ++sft, ++it) {
+              const int n_s = NT >> ((sft + 1) >> 1);
+              const int prefix = sft == 0 ? 0 : (sft == 1 ? NT : (sft == 2 ? NT + NT / 2 : 2 * NT));
+              const uint32_t s = it % S;
+              const uint32_t ph = (it / S) & 1;
+              mbar_wait(&empty[s], ph ^ 1);
+              uint8_t* sa = stage_base + s * Cfg::kStageBytes;
+              mbar_expect_tx(&full[s], a_bytes + n_s * 128);
+              tma_load_5d(sa, &tmap, &full[s], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
+              bulk_g2s(sa + kABytes, wkc + static_cast<size_t>(prefix) * 128, n_s * 128, &full[s]);
+            }
+          }
+        } else {
+          const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
+            const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
+            for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+              const uint32_t s = it % S;
+              const uint32_t ph = (it / S) & 1;
+              mbar_wait(&empty[s], ph ^ 1);
+              uint8_t* sa = stage_base + s * Cfg::kStageBytes;
+              mbar_expect_tx(&full[s], a_bytes + Cfg::kBBytes);
+              tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
+              bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(tap * p.kchunks + kc) * (NT * 64), Cfg::kBBytes,
+                       &full[s]);
+            }
           }
         }
       }
@@ -119,8 +151,8 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
-      constexpr uint32_t kALbo = kTileM * 16, kBLbo = NT * 16;
+      // A stage image: [plane][chunk][row][8] with `rows` dense rows per chunk (the TMA box), rows <= 128
+      const uint32_t a_lbo = static_cast<uint32_t>(p.rows) * 16, a_plane = a_lbo * 4;
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -128,6 +160,12 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
         for (int k = 0; k < k_iters; ++k, ++it) {
+          // scatter mode: k = kc * 4 + shift; the shift's weight slab has n_s rows and lands in column block `coloff`
+          const int sft = p.mode == 2 ? (k & 3) : 0;
+          const uint32_t n_s = p.mode == 2 ? (NT >> ((sft + 1) >> 1)) : NT;
+          const uint32_t coloff = (p.mode == 2 && sft >= 2) ? NT / 4 : 0;
+          const uint32_t idesc = umma_idesc(p.fmt, kTileM, static_cast<int>(n_s));
+          const uint32_t b_lbo = n_s * 16, b_plane = n_s * 64;
           const uint32_t s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&full[s], ph);
@@ -136,13 +174,13 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int j = 0; j < kBlockK / 16; ++j) {
-            const uint64_t a_hi = umma_desc(a_addr + j * 2 * kALbo, kALbo, 128);
-            const uint64_t a_lo = umma_desc(a_addr + kABytes / 2 + j * 2 * kALbo, kALbo, 128);
-            const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
-            const uint64_t b_lo = umma_desc(b_addr + Cfg::kBBytes / 2 + j * 2 * kBLbo, kBLbo, 128);
-            umma_bf16(d_tmem, a_lo, b_hi, idesc, (k | j) != 0);
-            umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-            umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+            const uint64_t a_hi = umma_desc(a_addr + j * 2 * a_lbo, a_lbo, 128);
+            const uint64_t a_lo = umma_desc(a_addr + a_plane + j * 2 * a_lbo, a_lbo, 128);
+            const uint64_t b_hi = umma_desc(b_addr + j * 2 * b_lbo, b_lbo, 128);
+            const uint64_t b_lo = umma_desc(b_addr + b_plane + j * 2 * b_lbo, b_lbo, 128);
+            umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, (k | j) != 0);
+            umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc, 1);
+            umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, 1);
           }
           umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
         }
@@ -164,7 +202,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
       const int b = tc.tb * p.bb + bl;
       const int y = tc.ty * p.bh + yy;
       const int x = tc.tx * p.bw + xx;
-      const bool valid = b < p.B && y < p.H && x < p.W;     // partial tiles: TMA zero-fills, stores are masked
+      const bool valid = r < p.rows && b < p.B && y < p.H && x < p.W;   // partial tiles: TMA zero-fills, stores are masked
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -174,6 +212,24 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * NT + c, v);
         tmem_ld_wait();
+        if (p.mode == 2) {
+          // raw parity planes t[b][plane][cout/8][H+1][W+1][8] (fp32); 32 columns = 4 channel chunks of one plane
+          if (valid) {
+            constexpr int CT = NT / 4;
+            const int plane = c / CT;
+            const int o0 = tc.n_tile * CT + (c % CT);
+            const size_t chunk_stride = static_cast<size_t>(p.H) * p.W * 8;
+            float* tptr = p.t_out + ((static_cast<size_t>(b) * 4 + plane) * (p.cout >> 3) + (o0 >> 3)) * chunk_stride +
+                          (static_cast<size_t>(y) * p.W + x) * 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4* dst = reinterpret_cast<float4*>(tptr + q * chunk_stride);
+              dst[0] = make_float4(v[8 * q + 0], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]);
+              dst[1] = make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
+            }
+          }
+          continue;
+        }
         if (valid) {
           const int n0 = tc.n_tile * NT + c;
           const int phase = p.up ? n0 / p.cout : 0;
@@ -254,11 +310,12 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
       tc_fence_before();
       mbar_arrive(&tempty[as]);     // 128 arrivals release the accumulator buffer
       if (valid && p.rgb_coef) {
-        float* rptr = p.rgb_acc + ((static_cast<size_t>(b) * 3) * p.Hout + y) * p.Wout + x;
+        // one partial-sum slot per column tile (summed in a fixed order by torgb_tail_kernel: deterministic)
         const size_t cs = static_cast<size_t>(p.Hout) * p.Wout;
-        atomicAdd(rptr, rgb0);
-        atomicAdd(rptr + cs, rgb1);
-        atomicAdd(rptr + 2 * cs, rgb2);
+        float* rptr = p.rgb_part + ((static_cast<size_t>(tc.n_tile) * p.B + b) * 3) * cs + static_cast<size_t>(y) * p.Wout + x;
+        rptr[0] = rgb0;
+        rptr[cs] = rgb1;
+        rptr[2 * cs] = rgb2;
       }
     }
   }
@@ -359,6 +416,11 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
   return 0;
 }
 
+bool acc_comp_enabled() {
+  static const bool comp = [] { const char* e = getenv("SGR_ACC_COMP"); return !(e && e[0] == '0'); }();
+  return comp;
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 void tile_box(int h, int w, int* bw, int* bh, int* bb) {
@@ -368,6 +430,29 @@ void tile_box(int h, int w, int* bw, int* bh, int* bb) {
   *bw = std::min(pw, 16);
   *bh = std::min(ph, kTileM / *bw);
   *bb = kTileM / (*bw * *bh);
+}
+
+// Any dense box with bw*bh*bb <= 128 rows is a legal M tile (rows beyond the box are never stored): for grids that are
+// not powers of two (the (H+1)x(W+1) parity-plane grid of the scatter up-conv) pick the box that needs the fewest tiles.
+void tile_box_search(int batch, int h, int w, int* bw, int* bh, int* bb) {
+  // Measured on B200 (tools/gpu_layer_bench.py, SGR_UP_BOX sweep): time follows the tile count as long as a box row is
+  // >= 128 B (8 pixels); boxes folding the batch over 2x2-pixel patches are 2.5x slower.  So: fewest tiles among boxes with
+  // bw >= min(w, 8), batch folding only when a whole image fits one tile; ties -> wider rows.
+  long long best_tiles = -1;
+  int best_bw = 0;
+  const int min_bw = std::min(w, 8);
+  for (int cw = std::min(w, 32); cw >= min_bw; --cw) {
+    for (int ch = std::min(h, kTileM / cw); ch >= 1; --ch) {
+      int cb = 1;
+      if (cw >= w && ch >= h) cb = std::max(1, std::min(batch, kTileM / (cw * ch)));
+      const long long tiles = static_cast<long long>((w + cw - 1) / cw) * ((h + ch - 1) / ch) * ((batch + cb - 1) / cb);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && cw > best_bw)) {
+        best_tiles = tiles;
+        best_bw = cw;
+        *bw = cw; *bh = ch; *bb = cb;
+      }
+    }
+  }
 }
 
 // Column tile minimising rounds x per-tile MMA time (cycles per K=16 step: 128/64/48/40 for N=256/128/64/32; the two
@@ -411,33 +496,61 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
     set_error("modconv: up requires ksize 3");
     return 1;
   }
+  if (a->up < 0 || a->up > 2 || (a->up == 2 && (!a->t_scratch || !a->fir || !a->demod))) {
+    set_error("modconv: up must be 0, 1 (polyphase) or 2 (scatter + FIR; needs t_scratch, fir and demod)");
+    return 1;
+  }
   if (a->noise && !a->noise_weight) {
     set_error("modconv: noise without noise_weight");
     return 1;
   }
-  if (a->rgb_coef && (!a->rgb_acc || a->up)) {
-    set_error("modconv: fused ToRGB needs rgb_acc and a non-upsampling layer");
+  if (a->rgb_coef && (!a->rgb_partial || a->up)) {
+    set_error("modconv: fused ToRGB needs rgb_partial and a non-upsampling layer");
     return 1;
   }
   p->B = a->batch;
-  p->H = a->h_in;
-  p->W = a->w_in;
-  tile_box(a->h_in, a->w_in, &p->bw, &p->bh, &p->bb);
-  p->tiles_x = (a->w_in + p->bw - 1) / p->bw;
-  p->tiles_y = (a->h_in + p->bh - 1) / p->bh;
+  p->mode = a->up;
+  if (a->up == 2) {               // tiles walk the (H+1) x (W+1) parity-plane grid
+    p->H = a->h_in + 1;
+    p->W = a->w_in + 1;
+    tile_box_search(a->batch, p->H, p->W, &p->bw, &p->bh, &p->bb);
+    if (const char* e = getenv("SGR_UP_BOX")) {        // experiments: "bw,bh,bb"
+      int ebw = 0, ebh = 0, ebb = 0;
+      if (sscanf(e, "%d,%d,%d", &ebw, &ebh, &ebb) == 3 && ebw >= 1 && ebw <= 32 && ebh >= 1 && ebb >= 1 &&
+          ebw * ebh * ebb <= kTileM) {
+        p->bw = ebw; p->bh = ebh; p->bb = ebb;
+      }
+    }
+  } else {
+    p->H = a->h_in;
+    p->W = a->w_in;
+    tile_box(a->h_in, a->w_in, &p->bw, &p->bh, &p->bb);
+  }
+  p->rows = p->bw * p->bh * p->bb;
+  p->tiles_x = (p->W + p->bw - 1) / p->bw;
+  p->tiles_y = (p->H + p->bh - 1) / p->bh;
   p->tiles_b = (a->batch + p->bb - 1) / p->bb;
   p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
   const int n_total = a->cout * (a->up ? 4 : 1);
-  *nt = a->column_tile > 0 ? a->column_tile : pick_nt(n_total);
+  if (a->up == 2) {
+    *nt = up2_nt(a->cout);        // [oe|ee|eo|oo] blocks of NT/4 channels; fixed by the packed layout
+    if (a->column_tile > 0 && a->column_tile != *nt) {
+      set_error("modconv: scatter up-conv uses column tile %d for cout %d (got %d)", *nt, a->cout, a->column_tile);
+      return 1;
+    }
+  } else {
+    *nt = a->column_tile > 0 ? a->column_tile : pick_nt(n_total);
+  }
   if (*nt > n_total || n_total % *nt != 0 || (*nt != 32 && *nt != 64 && *nt != 128 && *nt != 256)) {
     set_error("modconv: column tile %d does not fit %d columns", *nt, n_total);
     return 1;
   }
   p->n_tiles = n_total / *nt;
   p->kchunks = a->cin / kBlockK;
-  p->ntaps = a->ksize * a->ksize;
+  p->ntaps = a->up == 2 ? 4 : a->ksize * a->ksize;
   p->cout = a->cout;
-  p->up = a->up ? 1 : 0;
+  p->up = a->up == 1 ? 1 : 0;
+  p->t_out = a->t_scratch;
   p->Hout = a->up ? 2 * a->h_in : a->h_in;
   p->Wout = a->up ? 2 * a->w_in : a->w_in;
   p->act = a->act;
@@ -451,8 +564,10 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->acc_scale = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
   // The tensor core's fp32 accumulate truncates: measured on B200 the result shrinks by ~1.16e-8 per MMA accumulated into
   // the same TMEM cell (tools/gpu_debug.py "mean signed rel err": -1.0e-5 at 864 MMAs, -1.6e-6 at 108).  Undo the mean.
-  static const bool comp = [] { const char* e = getenv("SGR_ACC_COMP"); return !(e && e[0] == '0'); }();
-  if (comp) p->acc_scale *= 1.f + 1.16e-8f * static_cast<float>(3 * a->ksize * a->ksize * (a->cin / 16));
+  const bool comp = acc_comp_enabled();
+  // (scatter up-conv: the parity planes see 4/2/2/1 taps; 9/4 on average over the 4 planes feeding each output)
+  const float mmas = a->up == 2 ? 3.f * 2.25f * (a->cin / 16) : static_cast<float>(3 * a->ksize * a->ksize * (a->cin / 16));
+  if (comp) p->acc_scale *= 1.f + 1.16e-8f * mmas;
   p->out_fmt = a->out_format;
   p->out_scale = act_scale(a->out_format);
   p->wpacked = static_cast<const __nv_bfloat16*>(a->w_packed);
@@ -465,7 +580,7 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->out_c8 = static_cast<__nv_bfloat16*>(a->out_c8);
   p->out_f32 = a->out_f32;
   p->rgb_coef = a->rgb_coef;
-  p->rgb_acc = a->rgb_acc;
+  p->rgb_part = a->rgb_partial;
   return 0;
 }
 

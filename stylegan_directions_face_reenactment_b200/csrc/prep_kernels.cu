@@ -84,6 +84,53 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   dst[4 * nt + row_in_plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Scatter up-conv packing (modconv_sm100.cu, mode 2).  Column tile = 4 parity blocks [oe|ee|eo|oo] of CT = nt/4 output
+// channels; shift s = (a,b) (a = s>>1 rows, b = s&1 columns) multiplies x[I-a, J-b] and owns the tap (ky,kx) =
+// (pu + 2a, pv + 2b) of every block whose parity (pu,pv) keeps that tap inside the 3x3 kernel:
+//   s=0: all four blocks (nt rows)   s=1: [oe|ee] (nt/2)   s=2: [ee|eo] (nt/2)   s=3: [ee] (nt/4)
+// conv_transpose2d semantics out[2i+ky, 2j+kx] += x[i,j] W[o,i,ky,kx] (model.py:248-254, no flip).
+// packed layout: [n_tile][kc][shift][plane][chunk(4)][n_local(n_s)][8]; one thread per 16-byte row.
+__global__ void pack_weight_up2_kernel(const float* __restrict__ w, int cout, int cin, int nt, float scale, int fmt,
+                                       float wscale, __nv_bfloat16* __restrict__ packed) {
+  const int ct = nt / 4;
+  const int kchunks = cin / kBlockK;
+  const int rows_per_kc = 9 * ct;                              // nt + nt/2 + nt/2 + nt/4
+  const long long rows = static_cast<long long>(cout / ct) * kchunks * rows_per_kc * 4;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows) return;
+  // decode: idx = ((ntile * 4chunks... ) keep it simple: enumerate (ntile, kc, chunk, r) with r in [0, 9ct)
+  long long t = idx;
+  const int r = static_cast<int>(t % rows_per_kc); t /= rows_per_kc;
+  const int chunk = static_cast<int>(t % 4); t /= 4;
+  const int kc = static_cast<int>(t % kchunks); t /= kchunks;
+  const int ntile = static_cast<int>(t);
+  int sft, nl;
+  if (r < nt) { sft = 0; nl = r; }
+  else if (r < nt + nt / 2) { sft = 1; nl = r - nt; }
+  else if (r < 2 * nt) { sft = 2; nl = r - nt - nt / 2; }
+  else { sft = 3; nl = r - 2 * nt; }
+  const int n_s = nt >> ((sft + 1) >> 1);
+  const int block = (sft >= 2 ? 1 : 0) + nl / ct;              // index into [oe, ee, eo, oo]
+  const int pu = (block == 0 || block == 3) ? 1 : 0;
+  const int pv = (block >= 2) ? 1 : 0;
+  const int ky = pu + 2 * (sft >> 1), kx = pv + 2 * (sft & 1);
+  const int o = ntile * ct + nl % ct;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i0 = kc * kBlockK + chunk * 8 + 2 * e;
+    const float v0 = scale * w[((static_cast<size_t>(o) * cin + i0) * 3 + ky) * 3 + kx];
+    const float v1 = scale * w[((static_cast<size_t>(o) * cin + i0 + 1) * 3 + ky) * 3 + kx];
+    split2(v0 * wscale, v1 * wscale, fmt, hi[e], lo[e]);
+  }
+  const int prefix = sft == 0 ? 0 : (sft == 1 ? nt : (sft == 2 ? nt + nt / 2 : 2 * nt));
+  // 16-byte row index of the slab (ntile, kc, sft); a slab row is 8 x 16 B (2 planes x 4 chunks)
+  const size_t slab = ((static_cast<size_t>(ntile) * kchunks + kc) * rows_per_kc + prefix) * 8;
+  uint4* dst = reinterpret_cast<uint4*>(packed) + slab;
+  dst[chunk * n_s + nl] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  dst[4 * n_s + chunk * n_s + nl] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 __global__ void wsq_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, float scale,
                            float* __restrict__ wsq) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,10 +285,25 @@ __global__ void const_input_kernel(const float* __restrict__ cinput, const float
 // ------------------------------------------------------------------------------------------------ host wrappers
 int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int ks, int up, int transpose, int fmt,
                        int nt_req, void* packed, float* wsq, cudaStream_t st) {
+  const float scale = 1.f / sqrtf(static_cast<float>(cin) * ks * ks);
+  if (up == 2 && !transpose) {
+    const int nt2 = up2_nt(cout);
+    const long long rows2 = static_cast<long long>(cout / (nt2 / 4)) * (cin / kBlockK) * (9 * nt2 / 4) * 4;
+    pack_weight_up2_kernel<<<static_cast<unsigned>((rows2 + 255) / 256), 256, 0, st>>>(
+        w, cout, cin, nt2, scale, fmt, w_scale(fmt), static_cast<__nv_bfloat16*>(packed));
+    count_launch();
+    if (!check_launch("pack_weight_up2_kernel")) return 1;
+    if (wsq) {
+      wsq_kernel<<<(cout * cin + 255) / 256, 256, 0, st>>>(w, cout, cin, ks * ks, scale, wsq);
+      count_launch();
+      if (!check_launch("wsq_kernel")) return 1;
+    }
+    return 0;
+  }
+  if (up) up = 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
   const int nt = nt_req > 0 ? nt_req : pick_nt(n_total);
-  const float scale = 1.f / sqrtf(static_cast<float>(cin) * ks * ks);
   const long long rows = static_cast<long long>(n_total) * ks * ks * (k_total / 8);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((rows + threads - 1) / threads);

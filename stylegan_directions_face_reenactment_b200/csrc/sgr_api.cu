@@ -64,7 +64,8 @@ struct SynthPlan {
   size_t style_off[SGR_MAX_STYLED], rgbstyle_off[SGR_MAX_RGB];
   size_t demod_off[SGR_MAX_STYLED], s2_off[SGR_MAX_STYLED], coef_off[SGR_MAX_STYLED];
   size_t rgbacc_off[SGR_MAX_RGB];
-  size_t rgbacc_begin, rgbacc_end;
+  int rgb_slots[SGR_MAX_RGB];
+  size_t t_off;
   size_t skip_off[2];
   size_t act_off[2];
   size_t total;
@@ -92,13 +93,24 @@ static int plan_synthesis(const sgr_synthesis* net, int batch, SynthPlan* pl) {
   for (int r = 0; r < net->n_rgb; ++r) {
     pl->rgbstyle_off[r] = off; off = align_up(off + B * net->rgb[r].cin * 4, 256);
   }
-  pl->rgbacc_begin = off;
   size_t max_act = 0;
   for (int r = 0; r < net->n_rgb; ++r) {
+    // one partial-sum slot per column tile of the conv that feeds this ToRGB (layer 0, 2, 4, ...)
+    const sgr_styled_layer& L = net->styled[r == 0 ? 0 : 2 * r];
+    const int nt = L.column_tile > 0 ? L.column_tile : pick_nt(L.cout);
+    pl->rgb_slots[r] = (L.cout + nt - 1) / nt;
     const size_t res = static_cast<size_t>(4) << r;
-    pl->rgbacc_off[r] = off; off = align_up(off + B * 3 * res * res * 4, 256);
+    pl->rgbacc_off[r] = off; off = align_up(off + pl->rgb_slots[r] * B * 3 * res * res * 4, 256);
   }
-  pl->rgbacc_end = off;
+  // parity planes of the scatter up-convs: [B][4][cout/8][H+1][W+1][8] fp32
+  size_t max_t = 0;
+  for (int l = 0; l < net->n_styled; ++l)
+    if (net->styled[l].up == 2) {
+      const size_t res_in = static_cast<size_t>(4) << ((l + 1) / 2 - 1);
+      const size_t e = B * 4 * net->styled[l].cout * (res_in + 1) * (res_in + 1) * 4;
+      if (e > max_t) max_t = e;
+    }
+  pl->t_off = off; off = align_up(off + max_t, 256);
   const size_t S = static_cast<size_t>(net->size);
   for (int i = 0; i < 2; ++i) {
     pl->skip_off[i] = off; off = align_up(off + B * 3 * S * S * 4, 256);
@@ -155,9 +167,14 @@ int sgr_choose_column_tile(int batch, int h_in, int w_in, int n_total) {
 }
 
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose) {
+  if (up == 2 && !transpose) return static_cast<size_t>(cout) * cin * 9 * 2 * 2;   // scatter: the 9 real taps
   const size_t n_total = transpose ? cin : static_cast<size_t>(cout) * (up ? 4 : 1);
   const size_t k_total = transpose ? static_cast<size_t>(cout) * (up ? 4 : 1) : cin;
   return n_total * k_total * ksize * ksize * 2 /*planes*/ * 2 /*bf16*/;
+}
+
+size_t sgr_up_scratch_bytes(int batch, int cout, int h_in, int w_in) {
+  return static_cast<size_t>(batch) * 4 * cout * (h_in + 1) * (w_in + 1) * 4;
 }
 
 int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int cin, int ksize, int up, int transpose,
@@ -165,6 +182,16 @@ int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int
   if (!have_device()) return 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
   const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
+  if (up == 2 && !transpose) {
+    if (!weight || !packed || ksize != 3 || cin % kBlockK != 0 || cout < 32 || (cout & (cout - 1)) != 0 ||
+        (format != SGR_FMT_BF16 && format != SGR_FMT_FP16) || (column_tile != 0 && column_tile != up2_nt(cout))) {
+      set_error("pack_modconv_weight: unsupported scatter up-conv cout=%d cin=%d k=%d tile=%d", cout, cin, ksize,
+                column_tile);
+      return 1;
+    }
+    return pack_weight_launch(weight, fir, cout, cin, ksize, 2, 0, format, column_tile, packed, wsq,
+                              static_cast<cudaStream_t>(stream));
+  }
   if (!weight || !packed || (up && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
       k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0 ||
       (format != SGR_FMT_BF16 && format != SGR_FMT_FP16) ||
@@ -196,8 +223,13 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
   const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
-  const int rc = launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+  int rc = launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
+  if (rc == 0 && args->up == 2) {
+    const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
+    const float comp = acc_comp_enabled() ? 1.16e-8f * 3.f * static_cast<float>(args->cin / 16) : 0.f;
+    rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream));
+  }
   return rc;
 }
 
@@ -296,11 +328,7 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
   }
   if (table_jobs_launch(tj, batch, st)) return 1;
 
-  // 3. zero the fused-ToRGB accumulators; modulated constant input
-  if (cudaMemsetAsync(ws + pl.rgbacc_begin, 0, pl.rgbacc_end - pl.rgbacc_begin, st) != cudaSuccess) {
-    set_error("synthesis_forward: memset failed");
-    return 1;
-  }
+  // 3. modulated constant input
   int cur = 0;
   if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, net->styled[0].cin, net->format,
                          ws + pl.act_off[cur], st))
@@ -340,7 +368,14 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     const int r = (l + 1) / 2;
     if (!L.up) {
       a.rgb_coef = F(pl.coef_off[l]);
-      a.rgb_acc = F(pl.rgbacc_off[r]);
+      a.rgb_partial = F(pl.rgbacc_off[r]);
+    } else if (L.up == 2) {
+      if (!L.fir) {
+        set_error("synthesis_forward: layer %d (scatter up-conv) lacks its blur kernel", l);
+        return 1;
+      }
+      a.fir = L.fir;
+      a.t_scratch = F(pl.t_off);
     }
     if (sgr_modconv_forward(&a, stream)) return 1;
     if (L.up) res *= 2;
@@ -352,7 +387,7 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
         set_error("synthesis_forward: rgb %d needs an upsample kernel", r);
         return 1;
       }
-      if (torgb_tail_launch(F(pl.rgbacc_off[r]), R.bias, prev_skip, R.fir, dst, batch, res, res, st)) return 1;
+      if (torgb_tail_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, dst, batch, res, res, st)) return 1;
       prev_skip = dst;
       skip_cur = 1 - skip_cur;
     }

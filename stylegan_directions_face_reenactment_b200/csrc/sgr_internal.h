@@ -23,8 +23,11 @@ inline float w_scale(int fmt) { return fmt == SGR_FMT_FP16 ? kWScaleFP16 : 1.f; 
 
 // GEMM column tile for a layer with n_total columns.
 inline int pick_nt(int n_total) { return n_total >= 256 ? 256 : n_total; }
+// Scatter up-conv: 4 parity blocks of NT/4 output channels per column tile.
+inline int up2_nt(int cout) { return cout >= 64 ? 256 : 4 * cout; }
 int choose_nt(int batch, int h, int w, int n_total);
 void tile_box(int h, int w, int* bw, int* bh, int* bb);
+void tile_box_search(int batch, int h, int w, int* bw, int* bh, int* bb);
 
 void set_error(const char* fmt, ...);
 void count_launch();
@@ -32,7 +35,9 @@ bool check_launch(const char* what);
 
 struct ConvKernelParams {
   int B, H, W;                  // pixel space of the implicit GEMM (input resolution)
-  int bw, bh, bb;               // tile box (bw*bh*bb == 128)
+  int mode;                     // 0 plain / 1x1, 1 polyphase up-conv, 2 scatter up-conv (raw parity planes -> t_out)
+  int bw, bh, bb;               // tile box (rows = bw*bh*bb <= 128)
+  int rows;
   int tiles_x, tiles_y, tiles_b;
   int m_tiles, n_tiles;
   int kchunks;                  // cin / 32
@@ -56,7 +61,8 @@ struct ConvKernelParams {
   __nv_bfloat16* out_c8;
   float* out_f32;
   const float* rgb_coef;
-  float* rgb_acc;
+  float* rgb_part;              // [n_tiles][B,3,H,W] partial ToRGB sums, one slot per column tile
+  float* t_out;                 // mode 2: [B][4][cout/8][H][W][8] fp32 parity planes (H, W = grid dims above)
 };
 
 // modconv_sm100.cu
@@ -106,7 +112,10 @@ int upfirdn2d_launch(const float* x, float* y, const float* taps, int planes, in
                      int pad0, int pad1, int kh, int kw, cudaStream_t st);
 int bias_act_launch(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
                     long long inner, int grad, float slope, float scale, cudaStream_t st);
-int torgb_tail_launch(const float* rgb_acc, const float* bias, const float* skip_in, const float* fir, float* out,
-                      int batch, int H, int W, cudaStream_t st);
+int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
+                      float* out, int batch, int H, int W, cudaStream_t st);
+// up_finish_sm100.cu: FIR + fused epilogue over the parity planes of a scatter up-conv
+int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st);
+bool acc_comp_enabled();
 
 }  // namespace sgr

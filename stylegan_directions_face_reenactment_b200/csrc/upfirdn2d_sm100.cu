@@ -217,9 +217,9 @@ int bias_act_launch(const float* x, const float* bias, const float* ref, float* 
 }
 
 // ------------------------------------------------------------------------------------------------ ToRGB tail
-// skip_out[b,c,y,x] = rgb_acc[b,c,y,x] + bias[c] + upfirdn2d(skip_in, fir, up=2, pad=(2,1))[b,c,y,x]   (model.py:355-359)
+// skip_out[b,c,y,x] = sum_slots rgb_partial[slot][b,c,y,x] + bias[c] + upfirdn2d(skip_in, fir, up=2, pad=(2,1))[b,c,y,x]   (model.py:355-359)
 // skip_in is [B,3,H/2,W/2] (or NULL for to_rgb1).  4 outputs per thread along x.
-__global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, const float* __restrict__ bias,
+__global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, int slots, const float* __restrict__ bias,
                                   const float* __restrict__ skip_in, const float* __restrict__ fir,
                                   float* __restrict__ out, int planes, int H, int W) {
   __shared__ float sk[16];
@@ -233,7 +233,11 @@ __global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, const float
     const int y = static_cast<int>((idx / (W / 4)) % H);
     const int pl = static_cast<int>(idx / (static_cast<long long>(W / 4) * H));
     const float b = __ldg(bias + pl % 3);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(rgb_acc + (static_cast<size_t>(pl) * H + y) * W + x0));
+    float4 a = __ldg(reinterpret_cast<const float4*>(rgb_acc + (static_cast<size_t>(pl) * H + y) * W + x0));
+    for (int s = 1; s < slots; ++s) {           // per-column-tile partial sums, fixed order
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(rgb_acc + ((static_cast<size_t>(s) * planes + pl) * H + y) * W + x0));
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w;
+    }
     float acc[4] = {a.x + b, a.y + b, a.z + b, a.w + b};
     if (skip_in) {
       const float* sp = skip_in + static_cast<size_t>(pl) * h2 * w2;
@@ -258,12 +262,12 @@ __global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, const float
   }
 }
 
-int torgb_tail_launch(const float* rgb_acc, const float* bias, const float* skip_in, const float* fir, float* out,
-                      int batch, int H, int W, cudaStream_t st) {
+int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
+                      float* out, int batch, int H, int W, cudaStream_t st) {
   const long long total4 = static_cast<long long>(batch) * 3 * H * (W / 4);
   const long long blocks = (total4 + 255) / 256;
   torgb_tail_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      rgb_acc, bias, skip_in, fir, out, batch * 3, H, W);
+      rgb_acc, slots, bias, skip_in, fir, out, batch * 3, H, W);
   count_launch();
   return check_launch("torgb_tail_kernel") ? 0 : 1;
 }

@@ -163,6 +163,10 @@ class ModulatedConv2d(nn.Module):
         if self._pack_cache.get('version') != version:          # parameter changed: every packed variant is stale
             self._pack_cache.clear()
             self._pack_cache['version'] = version
+        # upsampling layers: forward operator in scatter form (up=2: 9 real taps + FIR pass), adjoint in polyphase form
+        up_mode = 0 if not self.upsample else (1 if transpose else 2)
+        if up_mode == 2:
+            nt = 0                                               # fixed by the scatter layout
         slot = (bool(transpose), fmt, nt)
         hit = self._pack_cache.get(slot)
         if hit is not None:
@@ -178,11 +182,11 @@ class ModulatedConv2d(nn.Module):
             cin = wd.shape[1]                                # (the factor undoes the 1/sqrt(cin k^2) of the padded cin)
         wd = wd.contiguous().float()
         lib = N.lib()
-        nbytes = lib.sgr_packed_weight_bytes(cout, cin, ks, int(self.upsample), int(transpose))
+        nbytes = lib.sgr_packed_weight_bytes(cout, cin, ks, up_mode, int(transpose))
         packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if not transpose else None
         firc = None if fir is None else fir.detach().contiguous().float()
-        N.check(lib.sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, int(self.upsample), int(transpose),
+        N.check(lib.sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, up_mode, int(transpose),
                                             fmt, nt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
         self._pack_cache[slot] = (packed, wsq)
         return packed, wsq
@@ -224,10 +228,17 @@ def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
     out = torch.empty(b, cout_k, ho, wo, device=dev)
     a = N.ConvArgs()
     a.batch, a.cin, a.cout, a.h_in, a.w_in = b, cin, cout_k, h, w
-    a.ksize, a.up, a.act = conv.kernel_size, int(conv.upsample), int(act)
+    a.ksize, a.up, a.act = conv.kernel_size, 2 if conv.upsample else 0, int(act)
+    if conv.upsample:
+        if d is None:
+            d = torch.ones(b, cout_k, device=dev)
+        scratch = torch.empty(lib.sgr_up_scratch_bytes(b, cout_k, h, w), dtype=torch.uint8, device=dev)
+        firk = conv.blur.kernel.detach().contiguous().float()
+        a.t_scratch, a.fir = N.ptr(scratch), N.ptr(firk)
     a.act_gain = SQRT2 if act else 1.0
     a.operand_format = a.out_format = fmt
     a.x_c8, a.w_packed, a.demod = N.ptr(xc8), N.ptr(packed), N.ptr(d)
+    keep = (scratch, firk) if conv.upsample else None     # noqa: F841  (alive until the launches are enqueued)
     if bias is not None:
         bias = bias.detach().contiguous().float()
         a.bias = N.ptr(bias)

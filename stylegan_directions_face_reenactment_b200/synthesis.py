@@ -30,11 +30,14 @@ class NetDescriptor:
         for l, layer in enumerate(styled):
             conv = layer.conv
             d = s.styled[l]
-            d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, int(conv.upsample)
+            d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, 2 if conv.upsample else 0
             res_out = 4 << ((l + 1) // 2)
             res_in = res_out // 2 if conv.upsample else res_out
-            n_fwd = conv.out_channel * (4 if conv.upsample else 1)
-            d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, n_fwd)
+            if conv.upsample:                          # scatter layout: fixed column tile; FIR pass needs the blur taps
+                d.column_tile = 0
+                d.fir = self._p(conv.blur.kernel)
+            else:
+                d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.out_channel)
             packed, wsq = conv.packed(fmt=s.format, nt=d.column_tile)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
             d.w_packed, d.wsq = self._p(packed), self._p(wsq)

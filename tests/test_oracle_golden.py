@@ -118,3 +118,15 @@ def test_flop_model_matches_survey():
     assert abs(orc.forward_flops_per_frame(256, 1) / 1e9 - 29.794) < 0.01
     assert abs(orc.forward_flops_per_frame(256, 2) / 1e9 - 90.236) < 0.01
     assert abs(orc.forward_flops_per_frame(1024, 2) / 1e9 - 148.520) < 0.01
+
+
+def test_scatter_upconv_algebra_matches_reference_form():
+    """The parity-plane scatter + FIR bookkeeping the sm_100a kernels implement (csrc/modconv_sm100.cu mode 2,
+    csrc/up_finish_sm100.cu) equals conv_transpose2d(stride 2) + upfirdn2d(pad=(1,1)) (model.py:246-257) in fp64."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'up_scatter_emulation_check', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools',
+                                                   'up_scatter_emulation_check.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main() < 1e-12
