@@ -3,6 +3,8 @@
 The fixtures under tests/golden/ were produced by oracle/make_golden.py, which imports the
 unmodified reference modules from /root/reference in the build container.  CPU only.
 """
+import os
+
 import numpy as np
 import torch
 
