@@ -78,7 +78,7 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
  * wsq:    [cout, cin] fp32 = sum_k (weight*scale)^2 for the demodulation mini-GEMM (may be NULL).
  */
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose);
-/* bytes of the fp32 parity-plane scratch an up == 2 convolution needs: [B][4][cout/8][h_in+1][w_in+1][8] */
+/* bytes of the fp32 parity-plane scratch an up == 2 convolution needs: [B][4][cout/4][h_in+1][w_in+1][4] */
 size_t sgr_up_scratch_bytes(int batch, int cout, int h_in, int w_in);
 /* GEMM column tile (32/64/128/256) the library would pick for a layer with n_total GEMM columns (cout, x4 for up
  * layers; cin for the adjoint) on an h_in x w_in grid at this batch: fills the 148 SMs on the small layers.  The packed

@@ -1,0 +1,258 @@
+// 3x3 modulated convolution on the sm_100a tensor cores with a RESIDENT halo tile (same math and epilogue as
+// modconv_sm100.cu; replaces the same reference code: model.py:232-287,331-337).
+//
+// modconv_sm100.cu loads the 128-pixel A tile once per tap (9 shifted TMA boxes per 32-channel block) and one weight
+// slab per 128 pixels.  On the wide, low-channel layers that makes the kernel L2 -> shared-memory bound.  Here:
+//   * one TMA box per 32-channel block brings the pixel tile WITH its one-pixel halo, (8*MT + 2) x 18 pixels, and all nine
+//     taps read it in place: in the no-swizzle K-major layout a pixel is one 16-byte row, the eight pixels of an image row
+//     are one core matrix (8 rows x 16 B, contiguous), image rows are SBO = (8*MT+2)*16 bytes apart and the 8-channel
+//     chunks LBO = box bytes apart, so tap (dy,dx) is just the descriptor start address + (dy*(8*MT+2) + dx)*16;
+//   * MT (1 or 2) horizontally adjacent 8x16-pixel tiles share every weight slab (MT accumulators of NT columns, double
+//     buffered in the 512 TMEM columns), halving the weight traffic of the NT <= 128 layers.
+// A-operand traffic drops from 9x to (8MT+2)*18 / (8MT*16) = 1.4x / 1.27x of the tile.
+//
+// Warp roles as in modconv_sm100.cu: warp0 TMA producer (A ring of 32-channel blocks + B ring of (block, tap) slabs),
+// warp1 MMA issuer, warp2 TMEM allocator, warps4-7 epilogue.
+#include <algorithm>
+#include <stdlib.h>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+#include "modconv_epilogue.cuh"
+
+namespace sgr {
+
+template <int NT, int MT>
+struct HaloCfg {
+  static constexpr int kTileW = 8 * MT, kTileH = 16;
+  static constexpr int kHW = kTileW + 2, kHH = kTileH + 2;
+  static constexpr int kChunkBytes = kHW * kHH * 16;          // one 8-channel chunk of the halo box
+  static constexpr int kABytes = kChunkBytes * 4 * 2;         // 32 channels x (hi, lo)
+  static constexpr int kBBytes = NT * kBlockK * 2 * 2;        // one (block, tap) weight slab, hi + lo
+  static constexpr int kAStages = 3;
+  static constexpr int kBRaw = (226 * 1024 - 1024 - kAStages * kABytes) / kBBytes;
+  static constexpr int kBStages = kBRaw > 8 ? 8 : kBRaw;
+  static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kBStages * kBBytes;
+  static_assert(kABytes % 128 == 0, "TMA destination alignment");
+  static_assert(kBStages >= 3, "weight ring too shallow");
+  static_assert(2 * MT * NT <= 512, "TMEM columns");
+};
+
+template <int NT, int MT>
+__global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                              const ConvKernelParams p) {
+  using Cfg = HaloCfg<NT, MT>;
+  constexpr int AS = Cfg::kAStages, BS = Cfg::kBStages;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* b_full = a_empty + AS;
+  uint64_t* b_empty = b_full + BS;
+  uint64_t* tfull = b_empty + BS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* a_base = smem + 1024;
+  uint8_t* b_base = a_base + AS * Cfg::kABytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < AS; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < BS; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / p.m_tiles;
+        int m = tile - n_tile * p.m_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int b = m / p.tiles_y;
+        const int x0 = tx * Cfg::kTileW - 1, y0 = ty * Cfg::kTileH - 1;
+        const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(n_tile) * 9 * p.kchunks * (NT * 64);
+        for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+          const uint32_t as = ai % AS;
+          mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
+          mbar_expect_tx(&a_full[as], Cfg::kABytes);
+          tma_load_5d(a_base + as * Cfg::kABytes, &tmap, &a_full[as], x0 * 8, y0, b, kb * 4, 0);
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const uint32_t bs = bi % BS;
+            mbar_wait(&b_empty[bs], ((bi / BS) & 1) ^ 1);
+            mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
+            bulk_g2s(b_base + bs * Cfg::kBBytes, wsrc + static_cast<size_t>(tap * p.kchunks + kb) * (NT * 64), Cfg::kBBytes,
+                     &b_full[bs]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
+      constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;
+      constexpr uint32_t kBLbo = NT * 16, kBPlane = NT * 64;
+      uint32_t ai = 0, bi = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (MT * NT);
+        for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+          const uint32_t as = ai % AS;
+          mbar_wait(&a_full[as], (ai / AS) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + as * Cfg::kABytes);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const uint32_t bs = bi % BS;
+            mbar_wait(&b_full[bs], (bi / BS) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(b_base + bs * Cfg::kBBytes);
+            const uint32_t tap_off = static_cast<uint32_t>((tap / 3) * Cfg::kHW + (tap % 3)) * 16;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint32_t a_off = a_addr + tap_off + mt * 128 + j * 2 * kALbo;
+                const uint64_t a_hi = umma_desc(a_off, kALbo, kASbo);
+                const uint64_t a_lo = umma_desc(a_off + kAPlane, kALbo, kASbo);
+                const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
+                const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
+                umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb | tap | j) != 0);
+                umma_bf16(d_tmem + mt * NT, a_hi, b_lo, idesc, 1);
+                umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
+              }
+            }
+            umma_commit(&b_empty[bs]);     // weight slab consumed
+          }
+          umma_commit(&a_empty[as]);       // halo block consumed by all nine taps
+        }
+        umma_commit(&tfull[acc]);          // accumulators complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;                  // tile row: pixel (r & 7, r >> 3) of each 8x16 sub-tile
+    const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+    const size_t plane_stride = static_cast<size_t>(p.B) * p.cout * p.Hout * p.Wout;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int n_tile = tile / p.m_tiles;
+      int m = tile - n_tile * p.m_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = m / p.tiles_y;
+      const int y = ty * Cfg::kTileH + (r >> 3);
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int x = tx * Cfg::kTileW + mt * 8 + (r & 7);
+        const bool valid = y < p.H && x < p.W;
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NT; c += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * MT + mt) * NT + c, v);
+          tmem_ld_wait();
+          if (valid) epilogue_32cols(p, v, n_tile * NT + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
+        }
+        if (valid && p.rgb_coef) rgb_store(p, n_tile, b, y, x, rgb0, rgb1, rgb2);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <int NT, int MT>
+static int launch_halo(const ConvKernelParams& p, const CUtensorMap& tmap, int sms, cudaStream_t stream) {
+  using Cfg = HaloCfg<NT, MT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(modconv_halo_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("modconv_halo: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  modconv_halo_kernel<NT, MT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, p);
+  count_launch();
+  return check_launch("modconv_halo_kernel") ? 0 : 1;
+}
+
+bool halo_eligible(const sgr_conv_args* a) {
+  static const bool off = [] { const char* e = getenv("SGR_HALO"); return e && e[0] == '0'; }();
+  if (off) return false;
+  return a->ksize == 3 && a->up == 0 && a->h_in >= 16 && a->w_in >= 16 && a->cout >= 32;
+}
+
+// Fills the tile geometry of `p` (already filled by conv_fill_params) for the halo kernel and launches it.
+int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    set_error("modconv_halo: no CUDA device");
+    return 1;
+  }
+  const int nt = a->column_tile > 0 ? a->column_tile : pick_nt(a->cout);
+  const int mt = nt <= 128 ? 2 : 1;
+  p.bw = 8 * mt; p.bh = 16; p.bb = 1; p.rows = 128;
+  p.tiles_x = (a->w_in + p.bw - 1) / p.bw;
+  p.tiles_y = (a->h_in + p.bh - 1) / p.bh;
+  p.tiles_b = a->batch;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  p.n_tiles = a->cout / nt;
+  CUtensorMap tmap;
+  if (make_act_tensor_map(&tmap, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw + 2, p.bh + 2, 1)) return 1;
+  switch (nt) {
+    case 256: return launch_halo<256, 1>(p, tmap, sms, stream);
+    case 128: return launch_halo<128, 2>(p, tmap, sms, stream);
+    case 64: return launch_halo<64, 2>(p, tmap, sms, stream);
+    case 32: return launch_halo<32, 2>(p, tmap, sms, stream);
+    default: set_error("modconv_halo: unsupported column tile %d", nt); return 1;
+  }
+}
+
+}  // namespace sgr

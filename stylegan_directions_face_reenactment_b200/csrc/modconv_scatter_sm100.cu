@@ -1,0 +1,267 @@
+// Upsampling modulated convolution, scatter form: conv_transpose2d(stride 2) (model.py:246-254) at its MINIMAL flop
+// count on the sm_100a tensor cores.  The (2H+1)^2 intermediate t[2i+ky, 2j+kx] += x[i,j] W[ky,kx] splits into four
+// parity planes on the (H+1) x (W+1) grid
+//   ee[I,J] = sum_{a,b} x[I-a,J-b] W[2a,2b]   eo[I,J] = sum_a x[I-a,J] W[2a,1]
+//   oe[I,J] = sum_b x[I,J-b] W[1,2b]          oo[I,J] = x[I,J] W[1,1]
+// i.e. four shifted activation tiles (shift s = (a,b)) times column blocks [oe|ee|eo|oo] of one accumulator: shift (0,0)
+// feeds all four blocks (N = NT), (0,1) feeds [oe|ee] (N = NT/2), (1,0) feeds [ee|eo] (N = NT/2), (1,1) feeds [ee]
+// (N = NT/4): 9 Cin Cout MACs per input pixel instead of the 36 of the polyphase form.  The raw planes go to HBM (fp32)
+// and up_finish_kernel applies the 4x4 FIR of the Blur (model.py:72-88) + the fused StyledConv epilogue.
+//
+// GEMM rows: a dense (bw x bh x bb) box of the parity grid, rows <= 128 (tile_box_search); TMA zero-fills x[-1], x[H].
+// Pipeline: the kernel is bound by bytes in flight between L2 and shared memory, so the activation tiles (ring of
+// 4 x 16 KiB, slot == shift) and the weight slabs (ring of kGroups channel blocks x [NT, NT/2, NT/2, NT/4] rows, exact
+// sizes) have separate rings and barriers.  The single MMA-issuing thread is the critical resource on the N = NT/4 and
+// NT/2 steps (6 MMAs of ~50 ns): its loop carries no division or descriptor construction - ring slots and phases follow
+// from the running channel-block counter, descriptors are base + offset adds.
+// Warp roles as in modconv_sm100.cu.
+#include <algorithm>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+
+namespace sgr {
+
+template <int NT>
+struct ScatterCfg {
+  static constexpr int kGroupRows = NT / 4 * 9;                          // weight rows per 32-channel block
+  static constexpr int kGroupBytes = kGroupRows * 128;
+  static constexpr int kGroups = (144 * 1024) / kGroupBytes;             // 2 (NT=256), 4 (NT=128)
+  static constexpr int kBSlabs = kGroups * 4;
+  static constexpr int kAStages = 4;                                      // one slot per shift: slot index == shift
+  static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+  static_assert(kBSlabs <= 16, "barrier block");
+};
+
+__device__ __forceinline__ int scatter_rows(int nt, int sft) { return nt >> ((sft + 1) >> 1); }          // NT, NT/2, NT/2, NT/4
+__device__ __forceinline__ int scatter_prefix(int nt, int sft) {                                          // rows before shift
+  return sft == 0 ? 0 : (sft == 1 ? nt : (sft == 2 ? nt + nt / 2 : 2 * nt));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                const ConvKernelParams p) {
+  using Cfg = ScatterCfg<NT>;
+  constexpr int AS = Cfg::kAStages, BSL = Cfg::kBSlabs;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* b_full = a_empty + AS;
+  uint64_t* b_empty = b_full + BSL;
+  uint64_t* tfull = b_empty + BSL;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* a_base = smem + 1024;
+  uint8_t* b_base = a_base + AS * kABytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < AS; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < BSL; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = 4 * p.kchunks;                  // k = kc * 4 + shift
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
+      uint32_t g = 0;                                  // running channel-block counter: ring slots and phases
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / p.m_tiles;
+        int m = tile - n_tile * p.m_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tb = m / p.tiles_y;
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+        const uint8_t* wkc = reinterpret_cast<const uint8_t*>(p.wpacked) +
+                             static_cast<size_t>(n_tile) * p.kchunks * Cfg::kGroupBytes;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++g, wkc += Cfg::kGroupBytes) {
+          const uint32_t grp = g % Cfg::kGroups;
+          const uint32_t a_par = (g & 1) ^ 1, b_par = ((g / Cfg::kGroups) & 1) ^ 1;
+          uint8_t* bdst = b_base + grp * Cfg::kGroupBytes;
+#pragma unroll
+          for (int sft = 0; sft < 4; ++sft) {
+            const int n_s = scatter_rows(NT, sft), prefix = scatter_prefix(NT, sft);
+            const uint32_t bs = grp * 4 + sft;
+            mbar_wait(&a_empty[sft], a_par);
+            mbar_expect_tx(&a_full[sft], a_bytes);
+            tma_load_5d(a_base + sft * kABytes, &tmap, &a_full[sft], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
+            mbar_wait(&b_empty[bs], b_par);
+            mbar_expect_tx(&b_full[bs], n_s * 128);
+            bulk_g2s(bdst + prefix * 128, wkc + prefix * 128, n_s * 128, &b_full[bs]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      // descriptors = base (LBO/SBO/version fields + ring base address) + byte offset >> 4
+      const uint32_t a_lbo = static_cast<uint32_t>(p.rows) * 16;
+      const uint64_t a_desc0 = umma_desc(smem_u32(a_base), a_lbo, 128);
+      const uint64_t a_lo_off = (a_lbo * 4) >> 4, a_j_off = (a_lbo * 2) >> 4;
+      uint64_t b_desc0[4];
+      uint32_t idesc[4];
+#pragma unroll
+      for (int sft = 0; sft < 4; ++sft) {
+        const uint32_t n_s = scatter_rows(NT, sft);
+        b_desc0[sft] = umma_desc(smem_u32(b_base) + scatter_prefix(NT, sft) * 128, n_s * 16, 128);
+        idesc[sft] = umma_idesc(p.fmt, kTileM, static_cast<int>(n_s));
+      }
+      uint32_t g = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * NT;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++g) {
+          const uint32_t grp = g % Cfg::kGroups;
+          const uint32_t a_par = g & 1, b_par = (g / Cfg::kGroups) & 1;
+          const uint64_t grp_off = (grp * Cfg::kGroupBytes) >> 4;
+#pragma unroll
+          for (int sft = 0; sft < 4; ++sft) {
+            const uint32_t n_s = scatter_rows(NT, sft);
+            const uint32_t coloff = sft >= 2 ? NT / 4 : 0;        // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
+            mbar_wait(&a_full[sft], a_par);
+            mbar_wait(&b_full[grp * 4 + sft], b_par);
+            tc_fence_after();
+            const uint64_t a_hi0 = a_desc0 + ((sft * kABytes) >> 4);
+            const uint64_t b_hi0 = b_desc0[sft] + grp_off;
+#pragma unroll
+            for (int j = 0; j < kBlockK / 16; ++j) {
+              const uint64_t a_hi = a_hi0 + j * a_j_off, a_lo = a_hi + a_lo_off;
+              const uint64_t b_hi = b_hi0 + j * ((n_s * 32) >> 4), b_lo = b_hi + ((n_s * 64) >> 4);
+              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc[sft], (kc | sft | j) != 0);
+              umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc[sft], 1);
+              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], 1);
+            }
+            umma_commit(&a_empty[sft]);
+            umma_commit(&b_empty[grp * 4 + sft]);
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: raw parity planes -> HBM
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;
+    const int xx = r % p.bw;
+    const int yy = (r / p.bw) % p.bh;
+    const int bl = r / (p.bw * p.bh);
+    constexpr int CT = NT / 4;
+    const size_t group_stride = static_cast<size_t>(p.H) * p.W * 4;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int n_tile = tile / p.m_tiles;
+      int m = tile - n_tile * p.m_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int tb = m / p.tiles_y;
+      const int b = tb * p.bb + bl, y = ty * p.bh + yy, x = tx * p.bw + xx;
+      const bool valid = r < p.rows && b < p.B && y < p.H && x < p.W;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      // TMEM loads are double buffered: the load of columns c+32.. is in flight while columns c.. are stored
+      float v[2][32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * NT;
+      if (p.debug & 2) {            // experiment: no TMEM reads, no stores
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        continue;
+      }
+      tmem_ld32(taddr, v[0]);
+#pragma unroll
+      for (int ci = 0; ci < NT / 32; ++ci) {
+        tmem_ld_wait();
+        if (ci + 1 < NT / 32) tmem_ld32(taddr + (ci + 1) * 32, v[(ci + 1) & 1]);
+        // t[b][plane][cout/4][H+1][W+1][4] (fp32): a lane (pixel) stores 16 B per 4-channel group, consecutive lanes are
+        // consecutive pixels -> every store instruction writes whole 32 B sectors (a [..][8] layout with 32 B per pixel
+        // and two half-sector stores per lane ran the epilogue at half the L2 write rate and stalled the MMA pipe)
+        if (valid && !(p.debug & 1)) {
+          const int c = ci * 32;
+          const int plane = c / CT;
+          const int o0 = n_tile * CT + (c % CT);
+          float* tptr = p.t_out + ((static_cast<size_t>(b) * 4 + plane) * (p.cout >> 2) + (o0 >> 2)) * group_stride +
+                        (static_cast<size_t>(y) * p.W + x) * 4;
+          const float* vv = v[ci & 1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(tptr + q * group_stride) = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NT>
+static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap, int sms, cudaStream_t stream) {
+  using Cfg = ScatterCfg<NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(upconv_scatter_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("upconv_scatter: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  upconv_scatter_kernel<NT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, p);
+  count_launch();
+  return check_launch("upconv_scatter_kernel") ? 0 : 1;
+}
+
+int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    set_error("upconv_scatter: no CUDA device");
+    return 1;
+  }
+  switch (nt) {
+    case 256: return launch_scatter_nt<256>(p, tmap, sms, stream);
+    case 128: return launch_scatter_nt<128>(p, tmap, sms, stream);
+    default: set_error("upconv_scatter: unsupported column tile %d", nt); return 1;
+  }
+}
+
+}  // namespace sgr

@@ -17,13 +17,8 @@
 // Shared-memory operand layout (no swizzle, K-major): [plane][chunk of 8 channels][row][8 bf16]; a row is 16 B,
 // rows are contiguous (SBO = 128 B per 8 rows), K chunks are LBO = rows*16 B apart.
 //
-// Upsampling layers, scatter mode (p.mode == 2): conv_transpose2d(stride 2) at its MINIMAL flop count.  The (2H+1)^2
-// intermediate t[2i+ky, 2j+kx] += x[i,j] W[ky,kx] splits into four parity planes on the (H+1)x(W+1) grid
-//   ee[I,J] = sum_{a,b} x[I-a,J-b] W[2a,2b]   eo[I,J] = sum_a x[I-a,J] W[2a,1]
-//   oe[I,J] = sum_b x[I,J-b] W[1,2b]          oo[I,J] = x[I,J] W[1,1]
-// i.e. four shifted A tiles (shift = (a,b)) times column blocks [oe|ee|eo|oo] of the accumulator: shift (0,0) feeds all
-// four blocks (N = NT), (0,1) feeds [oe|ee], (1,0) feeds [ee|eo], (1,1) feeds [ee]: 9 Cin Cout MACs per input pixel.  The
-// raw planes go to HBM (fp32) and up_finish_kernel applies the 4x4 FIR + the fused epilogue.
+// The scatter form of the upsampling layers (minimal flops) lives in modconv_scatter_sm100.cu; the resident-halo variant
+// for wide 3x3 layers in modconv_halo_sm100.cu.  This kernel serves 1x1, small-resolution 3x3, polyphase and adjoint GEMMs.
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp0 = TMA producer, warp1 = MMA issuer,
 // warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> registers -> fused demod/noise/bias/lrelu/style/ToRGB -> HBM).
@@ -34,6 +29,7 @@
 
 #include "sgr_internal.h"
 #include "sgr_ptx.cuh"
+#include "modconv_epilogue.cuh"
 
 namespace sgr {
 
@@ -109,27 +105,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         const TileCoord tc = decode_tile(p, tile);
         const int x0 = tc.tx * p.bw, y0 = tc.ty * p.bh, b0 = tc.tb * p.bb;
         const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
-        if (p.mode == 2) {
-          // scatter up-conv: 4 shifted activation tiles, weight slabs of NT, NT/2, NT/2, NT/4 rows
-          const uint8_t* wtile = reinterpret_cast<const uint8_t*>(p.wpacked) +
-                                 static_cast<size_t>(tc.n_tile) * p.kchunks * (NT / 4 * 9) * 128;
-          // k order: channel block outer, shift inner -> the four shifted boxes of a block hit the same L2 lines and the
-          // weight slabs [n_tile][kc][shift] stream linearly
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            const uint8_t* wkc = wtile + static_cast<size_t>(kc) * (NT / 4 * 9) * 128;
-            for (int sft = 0; sft < 4; ++sft, ++it) {
-              const int n_s = NT >> ((sft + 1) >> 1);
-              const int prefix = sft == 0 ? 0 : (sft == 1 ? NT : (sft == 2 ? NT + NT / 2 : 2 * NT));
-              const uint32_t s = it % S;
-              const uint32_t ph = (it / S) & 1;
-              mbar_wait(&empty[s], ph ^ 1);
-              uint8_t* sa = stage_base + s * Cfg::kStageBytes;
-              mbar_expect_tx(&full[s], a_bytes + n_s * 128);
-              tma_load_5d(sa, &tmap, &full[s], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
-              bulk_g2s(sa + kABytes, wkc + static_cast<size_t>(prefix) * 128, n_s * 128, &full[s]);
-            }
-          }
-        } else {
+        {
           const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
@@ -160,12 +136,9 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
         for (int k = 0; k < k_iters; ++k, ++it) {
-          // scatter mode: k = kc * 4 + shift; the shift's weight slab has n_s rows and lands in column block `coloff`
-          const int sft = p.mode == 2 ? (k & 3) : 0;
-          const uint32_t n_s = p.mode == 2 ? (NT >> ((sft + 1) >> 1)) : NT;
-          const uint32_t coloff = (p.mode == 2 && sft >= 2) ? NT / 4 : 0;
-          const uint32_t idesc = umma_idesc(p.fmt, kTileM, static_cast<int>(n_s));
-          const uint32_t b_lbo = n_s * 16, b_plane = n_s * 64;
+          constexpr uint32_t n_s = NT, coloff = 0;
+          const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
+          constexpr uint32_t b_lbo = n_s * 16, b_plane = n_s * 64;
           const uint32_t s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&full[s], ph);
@@ -212,111 +185,11 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * NT + c, v);
         tmem_ld_wait();
-        if (p.mode == 2) {
-          // raw parity planes t[b][plane][cout/8][H+1][W+1][8] (fp32); 32 columns = 4 channel chunks of one plane
-          if (valid) {
-            constexpr int CT = NT / 4;
-            const int plane = c / CT;
-            const int o0 = tc.n_tile * CT + (c % CT);
-            const size_t chunk_stride = static_cast<size_t>(p.H) * p.W * 8;
-            float* tptr = p.t_out + ((static_cast<size_t>(b) * 4 + plane) * (p.cout >> 3) + (o0 >> 3)) * chunk_stride +
-                          (static_cast<size_t>(y) * p.W + x) * 8;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4* dst = reinterpret_cast<float4*>(tptr + q * chunk_stride);
-              dst[0] = make_float4(v[8 * q + 0], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]);
-              dst[1] = make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
-            }
-          }
-          continue;
-        }
-        if (valid) {
-          const int n0 = tc.n_tile * NT + c;
-          const int phase = p.up ? n0 / p.cout : 0;
-          const int o0 = n0 & (p.cout - 1);
-          const int oy = p.up ? 2 * y + (phase >> 1) : y;
-          const int ox = p.up ? 2 * x + (phase & 1) : x;
-          const float nz = p.noise ? nw * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride + oy * p.Wout + ox) : 0.f;
-          const float* dptr = p.demod ? p.demod + static_cast<size_t>(b) * p.cout + o0 : nullptr;
-          const float* bptr = p.bias ? p.bias + o0 : nullptr;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 d4 = dptr ? __ldg(reinterpret_cast<const float4*>(dptr) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-            d4.x *= p.acc_scale; d4.y *= p.acc_scale; d4.z *= p.acc_scale; d4.w *= p.acc_scale;
-            float4 b4 = bptr ? __ldg(reinterpret_cast<const float4*>(bptr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float t0 = fmaf(v[4 * q + 0], d4.x, nz + b4.x);
-            float t1 = fmaf(v[4 * q + 1], d4.y, nz + b4.y);
-            float t2 = fmaf(v[4 * q + 2], d4.z, nz + b4.z);
-            float t3 = fmaf(v[4 * q + 3], d4.w, nz + b4.w);
-            if (p.act) {
-              t0 = fmaxf(t0, 0.2f * t0);
-              t1 = fmaxf(t1, 0.2f * t1);
-              t2 = fmaxf(t2, 0.2f * t2);
-              t3 = fmaxf(t3, 0.2f * t3);
-            }
-            v[4 * q + 0] = t0;
-            v[4 * q + 1] = t1;
-            v[4 * q + 2] = t2;
-            v[4 * q + 3] = t3;
-          }
-          if (p.rgb_coef) {
-            const float* cptr = p.rgb_coef + static_cast<size_t>(b) * 3 * p.cout + o0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 c0 = __ldg(reinterpret_cast<const float4*>(cptr) + q);
-              const float4 c1 = __ldg(reinterpret_cast<const float4*>(cptr + p.cout) + q);
-              const float4 c2 = __ldg(reinterpret_cast<const float4*>(cptr + 2 * p.cout) + q);
-              rgb0 = fmaf(v[4 * q], c0.x, fmaf(v[4 * q + 1], c0.y, fmaf(v[4 * q + 2], c0.z, fmaf(v[4 * q + 3], c0.w, rgb0))));
-              rgb1 = fmaf(v[4 * q], c1.x, fmaf(v[4 * q + 1], c1.y, fmaf(v[4 * q + 2], c1.z, fmaf(v[4 * q + 3], c1.w, rgb1))));
-              rgb2 = fmaf(v[4 * q], c2.x, fmaf(v[4 * q + 1], c2.y, fmaf(v[4 * q + 2], c2.z, fmaf(v[4 * q + 3], c2.w, rgb2))));
-            }
-          }
-          if (p.out_f32) {
-            float* optr = p.out_f32 + ((static_cast<size_t>(b) * p.cout + o0) * p.Hout + oy) * p.Wout + ox;
-            const size_t cs = static_cast<size_t>(p.Hout) * p.Wout;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) optr[j * cs] = v[j] * p.act_gain;
-          }
-          if (p.out_c8) {
-            const float* sptr = p.s2 ? p.s2 + static_cast<size_t>(b) * p.cout + o0 : nullptr;
-            // element offset of channel chunk (o0/8) of this pixel inside the hi plane
-            __nv_bfloat16* optr = p.out_c8 +
-                (((static_cast<size_t>(b) * (p.cout >> 3) + (o0 >> 3)) * p.Hout + oy) * p.Wout + ox) * 8;
-            const size_t chunk_stride = static_cast<size_t>(p.Hout) * p.Wout * 8;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float g[8];
-              if (sptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sptr) + 2 * q);
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sptr) + 2 * q + 1);
-                g[0] = s0.x; g[1] = s0.y; g[2] = s0.z; g[3] = s0.w;
-                g[4] = s1.x; g[5] = s1.y; g[6] = s1.z; g[7] = s1.w;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] *= p.out_scale;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = p.act_gain * p.out_scale;
-              }
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                split2(v[8 * q + 2 * e] * g[2 * e], v[8 * q + 2 * e + 1] * g[2 * e + 1], p.out_fmt, hi[e], lo[e]);
-              *reinterpret_cast<uint4*>(optr + q * chunk_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(optr + plane_stride + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-        }
+        if (valid) epilogue_32cols(p, v, tc.n_tile * NT + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);     // 128 arrivals release the accumulator buffer
-      if (valid && p.rgb_coef) {
-        // one partial-sum slot per column tile (summed in a fixed order by torgb_tail_kernel: deterministic)
-        const size_t cs = static_cast<size_t>(p.Hout) * p.Wout;
-        float* rptr = p.rgb_part + ((static_cast<size_t>(tc.n_tile) * p.B + b) * 3) * cs + static_cast<size_t>(y) * p.Wout + x;
-        rptr[0] = rgb0;
-        rptr[cs] = rgb1;
-        rptr[2 * cs] = rgb2;
-      }
+      if (valid && p.rgb_coef) rgb_store(p, tc.n_tile, b, y, x, rgb0, rgb1, rgb2);
     }
   }
 
@@ -510,6 +383,7 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   }
   p->B = a->batch;
   p->mode = a->up;
+  { const char* e = getenv("SGR_DEBUG"); p->debug = e ? atoi(e) : 0; }
   if (a->up == 2) {               // tiles walk the (H+1) x (W+1) parity-plane grid
     p->H = a->h_in + 1;
     p->W = a->w_in + 1;

@@ -220,10 +220,18 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   ConvKernelParams p;
   int nt = 0;
   if (conv_fill_params(args, &p, &nt)) return 1;
+  int rc;
+  if (halo_eligible(args)) {           // wide 3x3 layers: resident halo tile (modconv_halo_sm100.cu)
+    const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
+    rc = launch_modconv_halo(args, p, static_cast<cudaStream_t>(stream));
+    if (prof) prof_end(static_cast<cudaStream_t>(stream));
+    return rc;
+  }
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
   const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
-  int rc = launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+  rc = args->up == 2 ? launch_upconv_scatter(p, tmap, nt, static_cast<cudaStream_t>(stream))
+                     : launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
   if (rc == 0 && args->up == 2) {
     const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));

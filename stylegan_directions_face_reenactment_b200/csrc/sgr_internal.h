@@ -35,6 +35,7 @@ bool check_launch(const char* what);
 
 struct ConvKernelParams {
   int B, H, W;                  // pixel space of the implicit GEMM (input resolution)
+  int debug;                    // experiment switches (SGR_DEBUG env)
   int mode;                     // 0 plain / 1x1, 1 polyphase up-conv, 2 scatter up-conv (raw parity planes -> t_out)
   int bw, bh, bb;               // tile box (rows = bw*bh*bb <= 128)
   int rows;
@@ -71,6 +72,11 @@ int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, c
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
                         int bb);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
+// modconv_scatter_sm100.cu: scatter-form upsampling convolution (parity planes -> p.t_out)
+int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
+// modconv_halo_sm100.cu: resident-halo variant for plain 3x3 layers of at least 16x16 pixels
+bool halo_eligible(const sgr_conv_args* a);
+int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream);
 
 // prep_kernels.cu
 struct StyleJob {

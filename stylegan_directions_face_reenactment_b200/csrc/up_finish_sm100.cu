@@ -17,7 +17,7 @@ namespace sgr {
 
 struct UpFinishParams {
   int B, C, H, W;              // input resolution; output is 2H x 2W; planes are (H+1) x (W+1)
-  const float* t;              // [B][4 (oe,ee,eo,oo)][C/8][H+1][W+1][8]
+  const float* t;              // [B][4 (oe,ee,eo,oo)][C/4][H+1][W+1][4]
   const float* fir;            // [4][4] blur.kernel
   const float* demod;          // [B,C]
   float plane_scale[4];        // undoes operand scales (+ accumulate-truncation compensation) per plane
@@ -42,7 +42,7 @@ struct UpFinishParams {
 //     the parity planes of one column, then a horizontal 4-tap pass over the column results of the lane neighbours;
 //   * a thread owns column n and 4 channels and walks down `rows` input rows with a 3-row register window, so every
 //     plane element is loaded once per thread column (one coalesced 16 B load per lane and plane per row);
-//   * lanes (2l, 2l+1) hold the two 4-channel halves of column n0-1+l: a warp covers 16 columns of which the inner 14
+//   * lanes l and l+16 hold the two 4-channel halves of column n0-1+l: a warp covers 16 columns of which the inner 14
 //     produce output, the two outer ones only feed their neighbours' horizontal taps through warp shuffles;
 //   * packed fp32x2 FMAs (FFMA2) halve the arithmetic issue slots.
 struct F4 {
@@ -71,7 +71,18 @@ __device__ __forceinline__ F4 f4_shfl(const F4& x, int src_lane) {
   return r;
 }
 
-__global__ void __launch_bounds__(128, 6) up_finish_kernel(const UpFinishParams p) {
+// bf16 hi/lo split of two values with paired conversions: hi = cvt.rn.bf16x2(v), lo = cvt.rn.bf16x2(v - float(hi))
+__device__ __forceinline__ void split_pair_bf16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ROWS: input rows walked by one warp (H % ROWS == 0, so the loop is uniform and the shuffles need no re-convergence code)
+template <int ROWS, int FMT, bool F32OUT>
+__global__ void __launch_bounds__(128, 5) up_finish_kernel(const UpFinishParams p) {
   // sc[0..3] = gy (vertical taps, flipped), sc[4..7] = gx (horizontal taps, flipped, normalised by the tap sum)
   __shared__ float sc[8];
   if (threadIdx.x < 4) {
@@ -87,125 +98,160 @@ __global__ void __launch_bounds__(128, 6) up_finish_kernel(const UpFinishParams 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane & 1, l = lane >> 1;
+  const int half = lane >> 4, l = lane & 15;              // lanes 0-15: channels 0-3 of the chunk, 16-31: channels 4-7
   const int strip = blockIdx.x % p.strips;
-  const int rgroup = (blockIdx.x / p.strips) * (blockDim.x >> 5) + warp;
-  const int m0 = rgroup * p.rows;
-  if (m0 >= p.H) return;                                   // whole warp
-  const int m1 = min(m0 + p.rows, p.H);
+  const int rgroup = (blockIdx.x / p.strips) * (blockDim.x >> 5) + warp;      // exact grid: always < H / ROWS
+  const int m0 = rgroup * ROWS;
   const int n = strip * 14 - 1 + l;
   const bool col_ok = n >= 0 && n <= p.W;                  // plane columns 0..W exist
   const bool out_ok = l >= 1 && l <= 14 && n < p.W;
   const int chunk = blockIdx.y, b = blockIdx.z;
   const int Hp = p.H + 1, Wp = p.W + 1;
   const int chunks = p.C >> 3;
-  const size_t plane_stride = static_cast<size_t>(chunks) * Hp * Wp * 8;
-  // planes in [oe, ee, eo, oo] order
-  const float* t_oe = p.t + (static_cast<size_t>(b) * 4 * chunks + chunk) * Hp * Wp * 8 + half * 4 + static_cast<size_t>(col_ok ? n : 0) * 8;
+  const size_t plane_stride = static_cast<size_t>(p.C >> 2) * Hp * Wp * 4;
+  const size_t row_stride = static_cast<size_t>(Wp) * 4;
+  // planes in [oe, ee, eo, oo] order; 4-channel group (chunk*2 + half); pointers sit on row m0
+  const float* t_oe = p.t + ((static_cast<size_t>(b) * 4 * (p.C >> 2)) + chunk * 2 + half) * Hp * Wp * 4 +
+                      static_cast<size_t>(col_ok ? n : 0) * 4 + static_cast<size_t>(m0) * row_stride;
   const float* t_ee = t_oe + plane_stride;
   const float* t_eo = t_ee + plane_stride;
   const float* t_oo = t_eo + plane_stride;
-  const size_t row_stride = static_cast<size_t>(Wp) * 8;
 
   // vertical coefficients with the per-plane scale folded in
-  const float gy0 = sc[0], gy1 = sc[1], gy2 = sc[2], gy3 = sc[3];
   const float gx0 = sc[4], gx1 = sc[5], gx2 = sc[6], gx3 = sc[7];
   const float s_oe = p.plane_scale[0], s_ee = p.plane_scale[1], s_eo = p.plane_scale[2], s_oo = p.plane_scale[3];
+  const float e0o = sc[0] * s_oe, e1e = sc[1] * s_ee, e2o = sc[2] * s_oe, e3e = sc[3] * s_ee;   // even column, py = 0
+  const float e0e = sc[0] * s_ee, e1o = sc[1] * s_oe, e2e = sc[2] * s_ee, e3o = sc[3] * s_oe;   // even column, py = 1
+  const float o0o = sc[0] * s_oo, o1e = sc[1] * s_eo, o2o = sc[2] * s_oo, o3e = sc[3] * s_eo;   // odd column, py = 0
+  const float o0e = sc[0] * s_eo, o1o = sc[1] * s_oo, o2e = sc[2] * s_eo, o3o = sc[3] * s_oo;   // odd column, py = 1
 
   const int c0 = chunk * 8 + half * 4;
   const int Ho = 2 * p.H, Wo = 2 * p.W;
-  float d[4], bi[4], g[4];
+  float2 d01, d23, b01, b23, g01, g23;
   {
     const float4 d0 = __ldg(reinterpret_cast<const float4*>(p.demod + static_cast<size_t>(b) * p.C + c0));
-    d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w;
+    d01 = make_float2(d0.x, d0.y); d23 = make_float2(d0.z, d0.w);
+    float bi[4], g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       bi[e] = p.bias ? __ldg(p.bias + c0 + e) : 0.f;
       g[e] = (p.s2 ? __ldg(p.s2 + static_cast<size_t>(b) * p.C + c0 + e) : p.act_gain) * p.out_scale;
     }
+    b01 = make_float2(bi[0], bi[1]); b23 = make_float2(bi[2], bi[3]);
+    g01 = make_float2(g[0], g[1]); g23 = make_float2(g[2], g[3]);
   }
   const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+  const float slope = p.act ? 0.2f : 1.f;
+  const float2 slope2 = make_float2(slope, slope);
   const size_t out_plane = static_cast<size_t>(p.B) * p.C * Ho * Wo;       // elements per hi/lo plane
+  // output pointers on row 2*m0: C8 pixel (2n + half) [lane `half` stores output pixel px == half], f32 row pair
+  __nv_bfloat16* o_c8 = p.out_c8 ? p.out_c8 + (((static_cast<size_t>(b) * chunks + chunk) * Ho + 2 * m0) * Wo + 2 * (out_ok ? n : 0) + half) * 8
+                                 : nullptr;
+  float* o_f32 = F32OUT ? p.out_f32 + ((static_cast<size_t>(b) * p.C + c0) * Ho + 2 * m0) * Wo + 2 * (out_ok ? n : 0) : nullptr;
+  const float* nz_ptr = p.noise ? p.noise + static_cast<size_t>(b) * p.noise_bstride + static_cast<size_t>(2 * m0) * Wo + 2 * (out_ok ? n : 0)
+                                : nullptr;
 
   // register window: odd planes at rows m-1, m; even planes at row m
-  F4 oe_m1 = f4_load(t_oe + static_cast<size_t>(m0 - 1) * row_stride, col_ok && m0 > 0);
-  F4 oo_m1 = f4_load(t_oo + static_cast<size_t>(m0 - 1) * row_stride, col_ok && m0 > 0);
-  F4 ee_0 = f4_load(t_ee + static_cast<size_t>(m0) * row_stride, col_ok);
-  F4 eo_0 = f4_load(t_eo + static_cast<size_t>(m0) * row_stride, col_ok);
-  F4 oe_0 = f4_load(t_oe + static_cast<size_t>(m0) * row_stride, col_ok);
-  F4 oo_0 = f4_load(t_oo + static_cast<size_t>(m0) * row_stride, col_ok);
+  F4 oe_m1 = f4_load(t_oe - row_stride, col_ok && m0 > 0);
+  F4 oo_m1 = f4_load(t_oo - row_stride, col_ok && m0 > 0);
+  F4 ee_0 = f4_load(t_ee, col_ok);
+  F4 eo_0 = f4_load(t_eo, col_ok);
+  F4 oe_0 = f4_load(t_oe, col_ok);
+  F4 oo_0 = f4_load(t_oo, col_ok);
 
-  for (int m = m0; m < m1; ++m) {
-    const size_t r1 = static_cast<size_t>(m + 1) * row_stride;             // row m+1 <= H always exists
-    const F4 ee_1 = f4_load(t_ee + r1, col_ok);
-    const F4 eo_1 = f4_load(t_eo + r1, col_ok);
-    const F4 oe_1 = f4_load(t_oe + r1, col_ok);
-    const F4 oo_1 = f4_load(t_oo + r1, col_ok);
+#pragma unroll 1
+  for (int i = 0; i < ROWS; ++i) {
+    t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;      // row m+1 <= H always exists
+    const F4 ee_1 = f4_load(t_ee, col_ok);
+    const F4 eo_1 = f4_load(t_eo, col_ok);
+    const F4 oe_1 = f4_load(t_oe, col_ok);
+    const F4 oo_1 = f4_load(t_oo, col_ok);
     // vertical pass: T rows 2m-1 .. 2m+3 of the even (2n) and odd (2n+1) column
     F4 ve[2], vo[2];
-    ve[0] = f4_fma(gy3 * s_ee, ee_1, f4_fma(gy2 * s_oe, oe_0, f4_fma(gy1 * s_ee, ee_0, f4_mul(gy0 * s_oe, oe_m1))));
-    ve[1] = f4_fma(gy3 * s_oe, oe_1, f4_fma(gy2 * s_ee, ee_1, f4_fma(gy1 * s_oe, oe_0, f4_mul(gy0 * s_ee, ee_0))));
-    vo[0] = f4_fma(gy3 * s_eo, eo_1, f4_fma(gy2 * s_oo, oo_0, f4_fma(gy1 * s_eo, eo_0, f4_mul(gy0 * s_oo, oo_m1))));
-    vo[1] = f4_fma(gy3 * s_oo, oo_1, f4_fma(gy2 * s_eo, eo_1, f4_fma(gy1 * s_oo, oo_0, f4_mul(gy0 * s_eo, eo_0))));
+    ve[0] = f4_fma(e3e, ee_1, f4_fma(e2o, oe_0, f4_fma(e1e, ee_0, f4_mul(e0o, oe_m1))));
+    ve[1] = f4_fma(e3o, oe_1, f4_fma(e2e, ee_1, f4_fma(e1o, oe_0, f4_mul(e0e, ee_0))));
+    vo[0] = f4_fma(o3e, eo_1, f4_fma(o2o, oo_0, f4_fma(o1e, eo_0, f4_mul(o0o, oo_m1))));
+    vo[1] = f4_fma(o3o, oo_1, f4_fma(o2e, eo_1, f4_fma(o1o, oo_0, f4_mul(o0e, eo_0))));
     oe_m1 = oe_0; oo_m1 = oo_0;
     ee_0 = ee_1; eo_0 = eo_1; oe_0 = oe_1; oo_0 = oo_1;
 
 #pragma unroll
     for (int py = 0; py < 2; ++py) {
-      // horizontal pass: columns 2n-1 .. 2n+2 (lane - 2 = column n-1, lane + 2 = column n+1; edge lanes are halo only)
-      const F4 vo_l = f4_shfl(vo[py], lane - 2);
-      const F4 ve_r = f4_shfl(ve[py], lane + 2);
-      const F4 vo_r = f4_shfl(vo[py], lane + 2);
+      // horizontal pass: columns 2n-1 .. 2n+2 (lane - 1 = column n-1, lane + 1 = column n+1; edge lanes are halo only)
+      const F4 vo_l = f4_shfl(vo[py], lane - 1);
+      const F4 ve_r = f4_shfl(ve[py], lane + 1);
+      const F4 vo_r = f4_shfl(vo[py], lane + 1);
       const F4 z0 = f4_fma(gx3, ve_r, f4_fma(gx2, vo[py], f4_fma(gx1, ve[py], f4_mul(gx0, vo_l))));
       const F4 z1 = f4_fma(gx3, vo_r, f4_fma(gx2, ve_r, f4_fma(gx1, vo[py], f4_mul(gx0, ve[py]))));
-      const float z[2][4] = {{z0.a.x, z0.a.y, z0.b.x, z0.b.y}, {z1.a.x, z1.a.y, z1.b.x, z1.b.y}};
-      const int oy = 2 * m + py;
-      float nz[2] = {0.f, 0.f};
-      if (p.noise && out_ok) {
-        const float2 nn = __ldg(reinterpret_cast<const float2*>(p.noise + static_cast<size_t>(b) * p.noise_bstride +
-                                                                 static_cast<size_t>(oy) * Wo + 2 * n));
-        nz[0] = nw * nn.x;
-        nz[1] = nw * nn.y;
+      float2 nz0 = b01, nz1 = b01, nz2 = b23, nz3 = b23;          // (px0: ch01, px1: ch01, px0: ch23, px1: ch23)
+      if (nz_ptr) {
+        const float2 nn = __ldg(reinterpret_cast<const float2*>(nz_ptr));
+        const float2 n0 = make_float2(nw * nn.x, nw * nn.x), n1 = make_float2(nw * nn.y, nw * nn.y);
+        nz0 = __fadd2_rn(b01, n0); nz1 = __fadd2_rn(b01, n1); nz2 = __fadd2_rn(b23, n0); nz3 = __fadd2_rn(b23, n1);
+        nz_ptr += Wo;
       }
-      float t[2][4];
-#pragma unroll
-      for (int px = 0; px < 2; ++px)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = fmaf(z[px][e], d[e], nz[px] + bi[e]);
-          if (p.act) v = fmaxf(v, 0.2f * v);
-          t[px][e] = v;
-        }
-      if (p.out_f32 && out_ok) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2* dst = reinterpret_cast<float2*>(p.out_f32 + ((static_cast<size_t>(b) * p.C + c0 + e) * Ho + oy) * Wo + 2 * n);
-          *dst = make_float2(t[0][e] * p.act_gain, t[1][e] * p.act_gain);
-        }
+      // t = z * demod + noise + bias ; leaky relu
+      float2 t0a = __ffma2_rn(z0.a, d01, nz0), t0b = __ffma2_rn(z0.b, d23, nz2);      // px 0: channels 01, 23
+      float2 t1a = __ffma2_rn(z1.a, d01, nz1), t1b = __ffma2_rn(z1.b, d23, nz3);      // px 1
+      {
+        const float2 s0a = __fmul2_rn(t0a, slope2), s0b = __fmul2_rn(t0b, slope2);
+        const float2 s1a = __fmul2_rn(t1a, slope2), s1b = __fmul2_rn(t1b, slope2);
+        t0a = make_float2(fmaxf(t0a.x, s0a.x), fmaxf(t0a.y, s0a.y)); t0b = make_float2(fmaxf(t0b.x, s0b.x), fmaxf(t0b.y, s0b.y));
+        t1a = make_float2(fmaxf(t1a.x, s1a.x), fmaxf(t1a.y, s1a.y)); t1b = make_float2(fmaxf(t1b.x, s1b.x), fmaxf(t1b.y, s1b.y));
       }
-      if (p.out_c8) {
+      if (F32OUT) {
+        if (out_ok) {
+          const size_t cs = static_cast<size_t>(Ho) * Wo;
+          const float ag = p.act_gain;
+          *reinterpret_cast<float2*>(o_f32) = make_float2(t0a.x * ag, t1a.x * ag);
+          *reinterpret_cast<float2*>(o_f32 + cs) = make_float2(t0a.y * ag, t1a.y * ag);
+          *reinterpret_cast<float2*>(o_f32 + 2 * cs) = make_float2(t0b.x * ag, t1b.x * ag);
+          *reinterpret_cast<float2*>(o_f32 + 3 * cs) = make_float2(t0b.y * ag, t1b.y * ag);
+        }
+        o_f32 += Wo;
+      }
+      if (o_c8) {
+        const float2 u0a = __fmul2_rn(t0a, g01), u0b = __fmul2_rn(t0b, g23), u1a = __fmul2_rn(t1a, g01), u1b = __fmul2_rn(t1b, g23);
         uint32_t hi[2][2], lo[2][2];
-#pragma unroll
-        for (int px = 0; px < 2; ++px)
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            split2(t[px][2 * e] * g[2 * e], t[px][2 * e + 1] * g[2 * e + 1], p.out_fmt, hi[px][e], lo[px][e]);
+        if (FMT == kFmtBF16) {
+          split_pair_bf16(u0a.x, u0a.y, hi[0][0], lo[0][0]);
+          split_pair_bf16(u0b.x, u0b.y, hi[0][1], lo[0][1]);
+          split_pair_bf16(u1a.x, u1a.y, hi[1][0], lo[1][0]);
+          split_pair_bf16(u1b.x, u1b.y, hi[1][1], lo[1][1]);
+        } else {
+          split2(u0a.x, u0a.y, FMT, hi[0][0], lo[0][0]);
+          split2(u0b.x, u0b.y, FMT, hi[0][1], lo[0][1]);
+          split2(u1a.x, u1a.y, FMT, hi[1][0], lo[1][0]);
+          split2(u1b.x, u1b.y, FMT, hi[1][1], lo[1][1]);
+        }
         // lane `half` keeps output pixel px == half and receives the partner lane's 4 channels of that pixel
         uint32_t rh[2], rl[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          rh[e] = __shfl_xor_sync(0xffffffffu, half ? hi[0][e] : hi[1][e], 1);
-          rl[e] = __shfl_xor_sync(0xffffffffu, half ? lo[0][e] : lo[1][e], 1);
+          rh[e] = __shfl_xor_sync(0xffffffffu, half ? hi[0][e] : hi[1][e], 16);
+          rl[e] = __shfl_xor_sync(0xffffffffu, half ? lo[0][e] : lo[1][e], 16);
         }
         if (out_ok) {
-          const size_t off = (((static_cast<size_t>(b) * chunks + chunk) * Ho + oy) * Wo + 2 * n + half) * 8;
           const uint4 h4 = half ? make_uint4(rh[0], rh[1], hi[1][0], hi[1][1]) : make_uint4(hi[0][0], hi[0][1], rh[0], rh[1]);
           const uint4 l4 = half ? make_uint4(rl[0], rl[1], lo[1][0], lo[1][1]) : make_uint4(lo[0][0], lo[0][1], rl[0], rl[1]);
-          *reinterpret_cast<uint4*>(p.out_c8 + off) = h4;
-          *reinterpret_cast<uint4*>(p.out_c8 + out_plane + off) = l4;
+          *reinterpret_cast<uint4*>(o_c8) = h4;
+          *reinterpret_cast<uint4*>(o_c8 + out_plane) = l4;
         }
+        o_c8 += static_cast<size_t>(Wo) * 8;
       }
     }
+  }
+}
+
+template <int ROWS>
+static void up_finish_dispatch(const UpFinishParams& p, dim3 grid, int threads, cudaStream_t st) {
+  const bool f32 = p.out_f32 != nullptr;
+  if (p.out_fmt == kFmtBF16) {
+    if (f32) up_finish_kernel<ROWS, kFmtBF16, true><<<grid, threads, 0, st>>>(p);
+    else up_finish_kernel<ROWS, kFmtBF16, false><<<grid, threads, 0, st>>>(p);
+  } else {
+    if (f32) up_finish_kernel<ROWS, kFmtFP16, true><<<grid, threads, 0, st>>>(p);
+    else up_finish_kernel<ROWS, kFmtFP16, false><<<grid, threads, 0, st>>>(p);
   }
 }
 
@@ -229,11 +275,22 @@ int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap
   p.out_c8 = static_cast<__nv_bfloat16*>(a->out_c8);
   p.out_f32 = a->out_f32;
   p.strips = (a->w_in + 13) / 14;
-  p.rows = a->h_in >= 64 ? 16 : (a->h_in >= 16 ? 8 : a->h_in);
-  const int rgroups = (a->h_in + p.rows - 1) / p.rows;
-  const int warps = rgroups < 4 ? rgroups : 4;
-  dim3 grid(p.strips * ((rgroups + warps - 1) / warps), a->cout / 8, a->batch);
-  up_finish_kernel<<<grid, warps * 32, 0, st>>>(p);
+  // rows per warp: long strips amortise the two preloaded window rows, short ones keep small layers parallel
+  int rows = a->h_in >= 64 ? 16 : (a->h_in >= 32 ? 8 : (a->h_in >= 8 ? 4 : 2));
+  while (a->h_in % rows != 0) rows >>= 1;            // any height: fall back to shorter strips (1 always divides)
+  p.rows = rows;
+  const int rgroups = a->h_in / rows;
+  int warps = 4;
+  while (rgroups % warps != 0) warps >>= 1;
+  dim3 grid(p.strips * (rgroups / warps), a->cout / 8, a->batch);
+  switch (rows) {
+    case 16: up_finish_dispatch<16>(p, grid, warps * 32, st); break;
+    case 8: up_finish_dispatch<8>(p, grid, warps * 32, st); break;
+    case 4: up_finish_dispatch<4>(p, grid, warps * 32, st); break;
+    case 2: up_finish_dispatch<2>(p, grid, warps * 32, st); break;
+    case 1: up_finish_dispatch<1>(p, grid, warps * 32, st); break;
+    default: set_error("up_finish: unsupported input height %d", a->h_in); return 1;
+  }
   count_launch();
   return check_launch("up_finish_kernel") ? 0 : 1;
 }
