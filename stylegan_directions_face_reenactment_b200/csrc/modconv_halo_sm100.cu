@@ -35,7 +35,12 @@ struct HaloCfg {
   static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kBStages * kBBytes;
   static_assert(kABytes % 128 == 0, "TMA destination alignment");
   static_assert(kBStages >= 3, "weight ring too shallow");
-  static_assert(2 * MT * NT <= 512, "TMEM columns");
+  // NT <= 64: an N = 64 MMA costs as much as N = 128 (the 128-row A operand read bounds it), so the three products of the
+  // hi/lo scheme are issued as A_hi x [W_hi | W_lo] (one N = 2 NT MMA into 2 NT columns) + A_lo x W_hi (N = NT); the
+  // epilogue adds the two column halves.
+  static constexpr bool kConcat = NT <= 64;
+  static constexpr int kAccCols = kConcat ? 2 * NT : NT;      // TMEM columns per sub-tile
+  static_assert(2 * MT * kAccCols <= 512, "TMEM columns");
 };
 
 template <int NT, int MT>
@@ -116,14 +121,16 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
+      const uint32_t idesc_cat = umma_idesc(p.fmt, kTileM, Cfg::kConcat ? 2 * NT : NT);
       constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;
-      constexpr uint32_t kBLbo = NT * 16, kBPlane = NT * 64;
+      // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64)
+      constexpr uint32_t kBLbo = Cfg::kConcat ? 2 * NT * 16 : NT * 16, kBPlane = Cfg::kConcat ? NT * 16 : NT * 64;
       uint32_t ai = 0, bi = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * NT);
+        const uint32_t d_tmem = tmem_base + acc * (MT * Cfg::kAccCols);
         for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
           const uint32_t as = ai % AS;
           mbar_wait(&a_full[as], (ai / AS) & 1);
@@ -144,10 +151,15 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
                 const uint64_t a_hi = umma_desc(a_off, kALbo, kASbo);
                 const uint64_t a_lo = umma_desc(a_off + kAPlane, kALbo, kASbo);
                 const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
-                const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
-                umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb | tap | j) != 0);
-                umma_bf16(d_tmem + mt * NT, a_hi, b_lo, idesc, 1);
-                umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
+                if (Cfg::kConcat) {
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, (kb | tap | j) != 0);   // hi*hi | hi*lo
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, idesc, 1);                         // lo*hi
+                } else {
+                  const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
+                  umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb | tap | j) != 0);
+                  umma_bf16(d_tmem + mt * NT, a_hi, b_lo, idesc, 1);
+                  umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
+                }
               }
             }
             umma_commit(&b_empty[bs]);     // weight slab consumed
@@ -183,8 +195,17 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
 #pragma unroll 1
         for (int c = 0; c < NT; c += 32) {
           float v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * MT + mt) * NT + c, v);
-          tmem_ld_wait();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * MT + mt) * Cfg::kAccCols + c;
+          tmem_ld32(taddr, v);
+          if (Cfg::kConcat) {
+            float w[32];
+            tmem_ld32(taddr + NT, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += w[e];
+          } else {
+            tmem_ld_wait();
+          }
           if (valid) epilogue_32cols(p, v, n_tile * NT + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
         }
         if (valid && p.rgb_coef) rgb_store(p, n_tile, b, y, x, rgb0, rgb1, rgb2);

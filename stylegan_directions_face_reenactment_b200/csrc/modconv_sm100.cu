@@ -136,9 +136,10 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
         for (int k = 0; k < k_iters; ++k, ++it) {
-          constexpr uint32_t n_s = NT, coloff = 0;
+          constexpr uint32_t coloff = 0;
           const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
-          constexpr uint32_t b_lbo = n_s * 16, b_plane = n_s * 64;
+          // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64, see pack_weight_kernel)
+          constexpr uint32_t b_lbo = NT <= 64 ? 2 * NT * 16 : NT * 16, b_plane = NT <= 64 ? NT * 16 : NT * 64;
           const uint32_t s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&full[s], ph);

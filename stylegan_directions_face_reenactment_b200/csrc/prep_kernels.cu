@@ -53,7 +53,7 @@ __device__ float effective_weight(const float* __restrict__ w, const float* __re
 }
 
 // One thread per 8-element (16 B) row of the packed image; writes the hi and the lo plane entry.
-// packed layout: [n_tile][tap][kc][plane][chunk(4)][n_local(NT)][8]
+// packed layout: [n_tile][tap][kc][plane][chunk(4)][n_local(NT)][8] for NT > 64, [n_tile][tap][kc][chunk][plane][n_local][8] for NT <= 64
 __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ fir, int cout, int cin,
                                    int ks, int up, int transpose, int n_total, int k_total, int nt, float scale,
                                    int fmt, float wscale, __nv_bfloat16* __restrict__ packed) {
@@ -80,8 +80,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
   const size_t slab = (static_cast<size_t>(ntile) * ntaps + tap) * kchunks + kc;        // stage index
   const size_t row_in_plane = static_cast<size_t>(chunk) * nt + nl;
   uint4* dst = reinterpret_cast<uint4*>(packed) + slab * (2 * 4 * nt);
-  dst[row_in_plane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  dst[4 * nt + row_in_plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  if (nt > 64) {                     // [plane][chunk][n]
+    dst[row_in_plane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[4 * nt + row_in_plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  } else {                           // [chunk][plane][n]: hi and lo rows of a chunk are adjacent, so [W_hi | W_lo] is ONE
+    dst[(2 * chunk) * nt + nl] = make_uint4(hi[0], hi[1], hi[2], hi[3]);          // 2*nt-row operand (modconv_halo_sm100.cu)
+    dst[(2 * chunk + 1) * nt + nl] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 // Scatter up-conv packing (modconv_sm100.cu, mode 2).  Column tile = 4 parity blocks [oe|ee|eo|oo] of CT = nt/4 output
@@ -146,7 +151,9 @@ __global__ void wsq_kernel(const float* __restrict__ w, int cout, int cin, int n
 
 // ------------------------------------------------------------------------------------------------ styles
 
-// One warp per (job, i): s[b,i] = <latent[b,row,:], W[i,:]> / sqrt(512) + bias[i]   (model.py:148-157 with lr_mul = 1)
+// One warp per (job, i, group of 4 samples): s[b,i] = <latent[b,row,:], W[i,:]> / sqrt(512) + bias[i]
+// (model.py:148-157 with lr_mul = 1).  The weight row stays in registers; the four samples are independent chains.
+constexpr int kStyleBatchGroup = 4;
 __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ latent, int latent_stride, int batch) {
   const StyleJob& j = jobs.job[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,47 +165,78 @@ __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ lat
   for (int q = 0; q < 4; ++q) wv[q] = __ldg(wrow + q * 32 + lane);
   const float bias = __ldg(j.mod_bias + i);
   const float scale = 0.044194173824159216f;   // 1/sqrt(512)
-  for (int b = 0; b < batch; ++b) {
+  const int b0 = blockIdx.z * kStyleBatchGroup;
+  float acc[kStyleBatchGroup];
+#pragma unroll
+  for (int u = 0; u < kStyleBatchGroup; ++u) {
+    acc[u] = 0.f;
+    const int b = min(b0 + u, batch - 1);
     const float4* lrow = reinterpret_cast<const float4*>(latent + static_cast<size_t>(b) * latent_stride +
                                                          static_cast<size_t>(j.latent_row) * SGR_STYLE_DIM);
-    float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 l = __ldg(lrow + q * 32 + lane);
-      acc = fmaf(l.x, wv[q].x, fmaf(l.y, wv[q].y, fmaf(l.z, wv[q].z, fmaf(l.w, wv[q].w, acc))));
+      acc[u] = fmaf(l.x, wv[q].x, fmaf(l.y, wv[q].y, fmaf(l.z, wv[q].z, fmaf(l.w, wv[q].w, acc[u]))));
     }
+  }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) j.out[static_cast<size_t>(b) * j.cin + i] = fmaf(acc, scale, bias);
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int u = 0; u < kStyleBatchGroup; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+  if (lane < kStyleBatchGroup && b0 + lane < batch) {
+    float v = acc[0];
+#pragma unroll
+    for (int u = 1; u < kStyleBatchGroup; ++u) v = lane == u ? acc[u] : v;
+    j.out[static_cast<size_t>(b0 + lane) * j.cin + i] = fmaf(v, scale, bias);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ demod + tables
 
-// One warp per (job, b, o).
-__global__ void table_kernel(const TableJobs jobs, int batch) {
-  const TableJob& j = jobs.job[blockIdx.z];
+// One warp per (job, o, group of 8 samples): the wsq row (<= 512 inputs) stays in registers and is reused by the samples
+// of the group, four samples at a time as independent chains (one warp per (b, o) re-read every row once per sample:
+// 270 MB of L2 traffic at B = 32).
+constexpr int kTableBatchGroup = 8;
+constexpr int kTableMaxCinPerLane = 16;          // cin <= 512
+__global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int batch) {
+  const TableJob& j = jobs.job[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + warp;
-  const int b = blockIdx.y;
   if (o >= j.cout) return;
-  const float* s = j.s + static_cast<size_t>(b) * j.cin;
   const float* q = j.wsq + static_cast<size_t>(o) * j.cin;
-  float acc = 0.f;
-  for (int i = lane; i < j.cin; i += 32) {
-    const float sv = __ldg(s + i);
-    acc = fmaf(sv * sv, __ldg(q + i), acc);
-  }
+  float wq[kTableMaxCinPerLane];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) {
-    const float kSqrt2 = 1.4142135623730951f;
-    j.demod[static_cast<size_t>(b) * j.cout + o] = rsqrtf(acc + 1e-8f);
-    if (j.s_next) j.s2[static_cast<size_t>(b) * j.cout + o] = kSqrt2 * __ldg(j.s_next + static_cast<size_t>(b) * j.cout + o);
-    if (j.s_rgb) {
-      const float sr = kSqrt2 * __ldg(j.s_rgb + static_cast<size_t>(b) * j.cout + o) * rsqrtf(static_cast<float>(j.cout));
-      for (int c = 0; c < 3; ++c)
-        j.rgb_coef[(static_cast<size_t>(b) * 3 + c) * j.cout + o] = sr * __ldg(j.w_rgb + c * j.cout + o);
+  for (int t = 0; t < kTableMaxCinPerLane; ++t) wq[t] = lane + 32 * t < j.cin ? __ldg(q + lane + 32 * t) : 0.f;
+  const int b0 = blockIdx.z * kTableBatchGroup;
+  const float kSqrt2 = 1.4142135623730951f;
+#pragma unroll 1
+  for (int bb = b0; bb < min(b0 + kTableBatchGroup, batch); bb += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < kTableMaxCinPerLane; ++t) {
+      if (32 * t < j.cin) {                       // warp-uniform
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = min(bb + u, batch - 1);
+          const float sv = lane + 32 * t < j.cin ? __ldg(j.s + static_cast<size_t>(b) * j.cin + lane + 32 * t) : 0.f;
+          acc[u] = fmaf(sv * sv, wq[t], acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+    if (lane < 4 && bb + lane < batch) {
+      const int b = bb + lane;
+      const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      j.demod[static_cast<size_t>(b) * j.cout + o] = rsqrtf(a + 1e-8f);
+      if (j.s_next) j.s2[static_cast<size_t>(b) * j.cout + o] = kSqrt2 * __ldg(j.s_next + static_cast<size_t>(b) * j.cout + o);
+      if (j.s_rgb) {
+        const float sr = kSqrt2 * __ldg(j.s_rgb + static_cast<size_t>(b) * j.cout + o) * rsqrtf(static_cast<float>(j.cout));
+        for (int c = 0; c < 3; ++c)
+          j.rgb_coef[(static_cast<size_t>(b) * 3 + c) * j.cout + o] = sr * __ldg(j.w_rgb + c * j.cout + o);
+      }
     }
   }
 }
@@ -322,7 +360,7 @@ int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int 
 int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st) {
   int cmax = 0;
   for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cin ? cmax : jobs.job[i].cin;
-  dim3 grid((cmax + 7) / 8, jobs.n);
+  dim3 grid((cmax + 7) / 8, jobs.n, (batch + kStyleBatchGroup - 1) / kStyleBatchGroup);
   style_kernel<<<grid, 256, 0, st>>>(jobs, latent, latent_stride, batch);
   count_launch();
   return check_launch("style_kernel") ? 0 : 1;
@@ -331,7 +369,12 @@ int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_str
 int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st) {
   int cmax = 0;
   for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cout ? cmax : jobs.job[i].cout;
-  dim3 grid((cmax + 7) / 8, batch, jobs.n);
+  for (int i = 0; i < jobs.n; ++i)
+    if (jobs.job[i].cin > 32 * kTableMaxCinPerLane) {
+      set_error("table_kernel: cin %d > %d unsupported", jobs.job[i].cin, 32 * kTableMaxCinPerLane);
+      return 1;
+    }
+  dim3 grid((cmax + 7) / 8, jobs.n, (batch + kTableBatchGroup - 1) / kTableBatchGroup);
   table_kernel<<<grid, 256, 0, st>>>(jobs, batch);
   count_launch();
   return check_launch("table_kernel") ? 0 : 1;
