@@ -130,7 +130,9 @@ typedef struct sgr_conv_args {
   const float* rgb_coef;  /* [B,3,cout] or NULL */
   float* rgb_partial;     /* [cout/column_tile][B,3,h_out,w_out], fully overwritten */
   float* t_scratch;       /* up == 2: sgr_up_scratch_bytes() of scratch */
-  const float* fir;       /* up == 2: blur.kernel [4,4] */
+  const float* fir;       /* up == 2: blur.kernel [4,4]; must be an outer product (rank 1), as make_kernel builds it */
+  int single_pass;        /* 0: split-precision products (3 MMAs, fp32 parity); 1: hi x hi only = plain bf16/fp16
+                             tensor-core precision with fp32 accumulation (BASELINE config 5), 1 MMA per product */
 } sgr_conv_args;
 int sgr_modconv_forward(const sgr_conv_args* args, void* stream);
 
@@ -177,6 +179,7 @@ typedef struct sgr_synthesis {
   int n_rgb;                 /* to_rgb1 + to_rgbs.* = log2(size) - 1 */
   int n_latent;
   int format;                /* SGR_FMT_* of the forward pass (w_packed of every layer must be packed with it) */
+  int single_pass;           /* see sgr_conv_args.single_pass; applies to every layer of sgr_synthesis_forward */
   const float* const_input;  /* [512,4,4] */
   sgr_styled_layer styled[SGR_MAX_STYLED];
   sgr_rgb_layer rgb[SGR_MAX_RGB];

@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
                 const uint64_t a_hi = umma_desc(a_off, kALbo, kASbo);
                 const uint64_t a_lo = umma_desc(a_off + kAPlane, kALbo, kASbo);
                 const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
-                if (Cfg::kConcat) {
+                if (p.single) {
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc, (kb | tap | j) != 0);
+                } else if (Cfg::kConcat) {
                   umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, (kb | tap | j) != 0);   // hi*hi | hi*lo
                   umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, idesc, 1);                         // lo*hi
                 } else {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
           float v[32];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + (acc * MT + mt) * Cfg::kAccCols + c;
           tmem_ld32(taddr, v);
-          if (Cfg::kConcat) {
+          if (Cfg::kConcat && !p.single) {
             float w[32];
             tmem_ld32(taddr + NT, w);
             tmem_ld_wait();

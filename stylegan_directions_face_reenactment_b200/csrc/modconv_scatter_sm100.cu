@@ -157,9 +157,13 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
             for (int j = 0; j < kBlockK / 16; ++j) {
               const uint64_t a_hi = a_hi0 + j * a_j_off, a_lo = a_hi + a_lo_off;
               const uint64_t b_hi = b_hi0 + j * ((n_s * 32) >> 4), b_lo = b_hi + ((n_s * 64) >> 4);
-              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc[sft], (kc | sft | j) != 0);
-              umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc[sft], 1);
-              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], 1);
+              if (!p.single) {
+                umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc[sft], (kc | sft | j) != 0);
+                umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc[sft], 1);
+                umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], 1);
+              } else {
+                umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], (kc | sft | j) != 0);
+              }
             }
             umma_commit(&a_empty[sft]);
             umma_commit(&b_empty[grp * 4 + sft]);

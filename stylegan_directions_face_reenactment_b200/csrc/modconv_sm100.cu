@@ -152,9 +152,13 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
             const uint64_t a_lo = umma_desc(a_addr + a_plane + j * 2 * a_lbo, a_lbo, 128);
             const uint64_t b_hi = umma_desc(b_addr + j * 2 * b_lbo, b_lbo, 128);
             const uint64_t b_lo = umma_desc(b_addr + b_plane + j * 2 * b_lbo, b_lbo, 128);
-            umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, (k | j) != 0);
-            umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc, 1);
-            umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, 1);
+            if (!p.single) {
+              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, (k | j) != 0);
+              umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc, 1);
+              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, 1);
+            } else {
+              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, (k | j) != 0);
+            }
           }
           umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
         }
@@ -436,12 +440,14 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
     return 1;
   }
   p->fmt = a->operand_format;
+  p->single = a->single_pass ? 1 : 0;
   p->acc_scale = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
   // The tensor core's fp32 accumulate truncates: measured on B200 the result shrinks by ~1.16e-8 per MMA accumulated into
   // the same TMEM cell (tools/gpu_debug.py "mean signed rel err": -1.0e-5 at 864 MMAs, -1.6e-6 at 108).  Undo the mean.
   const bool comp = acc_comp_enabled();
   // (scatter up-conv: the parity planes see 4/2/2/1 taps; 9/4 on average over the 4 planes feeding each output)
-  const float mmas = a->up == 2 ? 3.f * 2.25f * (a->cin / 16) : static_cast<float>(3 * a->ksize * a->ksize * (a->cin / 16));
+  const float per_product = a->single_pass ? 1.f : 3.f;
+  const float mmas = a->up == 2 ? per_product * 2.25f * (a->cin / 16) : per_product * a->ksize * a->ksize * (a->cin / 16);
   if (comp) p->acc_scale *= 1.f + 1.16e-8f * mmas;
   p->out_fmt = a->out_format;
   p->out_scale = act_scale(a->out_format);

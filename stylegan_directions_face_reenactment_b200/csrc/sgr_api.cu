@@ -235,7 +235,7 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
   if (rc == 0 && args->up == 2) {
     const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
-    const float comp = acc_comp_enabled() ? 1.16e-8f * 3.f * static_cast<float>(args->cin / 16) : 0.f;
+    const float comp = acc_comp_enabled() ? 1.16e-8f * (args->single_pass ? 1.f : 3.f) * static_cast<float>(args->cin / 16) : 0.f;
     rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream));
   }
   return rc;
@@ -361,6 +361,7 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     a.act = 1;
     a.act_gain = 1.4142135623730951f;
     a.operand_format = net->format;
+    a.single_pass = net->single_pass;
     a.column_tile = L.column_tile;
     a.out_format = net->format;
     a.x_c8 = ws + pl.act_off[cur];

@@ -49,6 +49,7 @@ struct ConvKernelParams {
   int act;
   float act_gain;
   int fmt;                      // operand format of x_c8 / wpacked (SGR_FMT_*)
+  int single;                   // 1: hi x hi products only (plain bf16/fp16 tensor-core precision, 1 MMA instead of 3)
   float acc_scale;              // undoes the operand scales on the accumulator
   int out_fmt;                  // format of out_c8
   float out_scale;              // activation scale of out_fmt

@@ -152,6 +152,24 @@ class ModulatedConv2d(nn.Module):
             new.__dict__[k] = {} if k == '_pack_cache' else copy.deepcopy(v, memo)
         return new
 
+    def up_mode(self):
+        """Packing / execution mode of an upsampling layer's forward operator: 2 (scatter conv + separable FIR pass) when
+        blur.kernel is an outer product (always true for kernels built by make_kernel from 1-D taps, reference
+        model.py:19-27), else 1 (polyphase folding, which takes any 4x4 FIR).  Checked once per buffer version."""
+        if not self.upsample:
+            return 0
+        k = self.blur.kernel
+        key = _version_key(k)
+        cache = self.__dict__.setdefault('_fir_cache', {})       # survives weight updates (only blur.kernel matters)
+        if cache.get('fir_key') != key:
+            kc = k.detach().double().cpu()
+            tot = kc.sum()
+            sep = torch.outer(kc.sum(1), kc.sum(0)) / tot if tot != 0 else torch.zeros_like(kc)
+            rank1 = tuple(kc.shape) == (4, 4) and bool((kc - sep).abs().max() <= 1e-6 * kc.abs().max())
+            cache['fir_key'] = key
+            cache['fir_mode'] = 2 if rank1 else 1
+        return cache['fir_mode']
+
     def packed(self, transpose=False, fmt=None, nt=0):
         """(w_packed, wsq) device tensors for the tcgen05 kernel; repacked when the parameter changes.
         The adjoint (transpose) is always packed as bf16 hi/lo: it multiplies gradients (csrc/backward.cu).
@@ -164,10 +182,10 @@ class ModulatedConv2d(nn.Module):
             self._pack_cache.clear()
             self._pack_cache['version'] = version
         # upsampling layers: forward operator in scatter form (up=2: 9 real taps + FIR pass), adjoint in polyphase form
-        up_mode = 0 if not self.upsample else (1 if transpose else 2)
+        up_mode = 0 if not self.upsample else (1 if transpose else self.up_mode())
         if up_mode == 2:
             nt = 0                                               # fixed by the scatter layout
-        slot = (bool(transpose), fmt, nt)
+        slot = (bool(transpose), fmt, nt, up_mode)
         hit = self._pack_cache.get(slot)
         if hit is not None:
             return hit
@@ -228,8 +246,9 @@ def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
     out = torch.empty(b, cout_k, ho, wo, device=dev)
     a = N.ConvArgs()
     a.batch, a.cin, a.cout, a.h_in, a.w_in = b, cin, cout_k, h, w
-    a.ksize, a.up, a.act = conv.kernel_size, 2 if conv.upsample else 0, int(act)
-    if conv.upsample:
+    a.ksize, a.up, a.act = conv.kernel_size, conv.up_mode(), int(act)
+    a.single_pass = N.single_pass()
+    if conv.up_mode() == 2:
         if d is None:
             d = torch.ones(b, cout_k, device=dev)
         scratch = torch.empty(lib.sgr_up_scratch_bytes(b, cout_k, h, w), dtype=torch.uint8, device=dev)
@@ -238,7 +257,7 @@ def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
     a.act_gain = SQRT2 if act else 1.0
     a.operand_format = a.out_format = fmt
     a.x_c8, a.w_packed, a.demod = N.ptr(xc8), N.ptr(packed), N.ptr(d)
-    keep = (scratch, firk) if conv.upsample else None     # noqa: F841  (alive until the launches are enqueued)
+    keep = (scratch, firk) if conv.up_mode() == 2 else None     # noqa: F841  (alive until the launches are enqueued)
     if bias is not None:
         bias = bias.detach().contiguous().float()
         a.bias = N.ptr(bias)

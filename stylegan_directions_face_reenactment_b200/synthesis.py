@@ -26,18 +26,19 @@ class NetDescriptor:
         rgbs = g.rgb_layers()
         s.size, s.n_styled, s.n_rgb, s.n_latent = g.size, len(styled), len(rgbs), g.n_latent
         s.format = N.default_format()
+        s.single_pass = 0 if backward else N.single_pass()
         s.const_input = self._p(g.input.input)
         for l, layer in enumerate(styled):
             conv = layer.conv
             d = s.styled[l]
-            d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, 2 if conv.upsample else 0
+            d.cin, d.cout, d.up = conv.in_channel, conv.out_channel, conv.up_mode()
             res_out = 4 << ((l + 1) // 2)
             res_in = res_out // 2 if conv.upsample else res_out
-            if conv.upsample:                          # scatter layout: fixed column tile; FIR pass needs the blur taps
+            if d.up == 2:                              # scatter layout: fixed column tile; FIR pass needs the blur taps
                 d.column_tile = 0
                 d.fir = self._p(conv.blur.kernel)
-            else:
-                d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.out_channel)
+            else:                                      # plain layers, or polyphase fallback for a non-separable FIR
+                d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.out_channel * (4 if d.up else 1))
             packed, wsq = conv.packed(fmt=s.format, nt=d.column_tile)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
             d.w_packed, d.wsq = self._p(packed), self._p(wsq)

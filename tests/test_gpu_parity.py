@@ -359,3 +359,55 @@ def test_train_step_config4_shapes(pkg):
     loss, nbytes = sdist.train_step(G, A, opt, w_src, dp, 0.7, trunc, lambda img: (img - tgt).abs().mean())
     assert torch.isfinite(loss) and nbytes == 0 and not torch.equal(before, A.linear.weight)
     assert tuple(src.shape) == (batch, 3, size, size)
+
+
+def test_upsample_non_separable_fir_falls_back_to_polyphase(pkg):
+    """The scatter + separable-FIR path needs a rank-1 blur kernel; any other 4x4 FIR must still be exact (polyphase)."""
+    import math
+    import torch.nn.functional as F
+    rng = np.random.Generator(np.random.PCG64(12))
+    m = pkg.StyledConv(64, 32, 3, 512, upsample=True).cuda()
+    assert m.conv.up_mode() == 2
+    x = T(rng.standard_normal((2, 64, 8, 8), dtype=np.float32))
+    w = T(rng.standard_normal((2, 512), dtype=np.float32))
+    nz = T(rng.standard_normal((2, 1, 16, 16), dtype=np.float32))
+
+    def reference(sd, fir):                                   # model.py:232-257,331-337 with an arbitrary blur buffer
+        b, cin, h, _ = x.shape
+        s = orc.equal_linear(w, sd['conv.modulation.weight'], sd['conv.modulation.bias']).view(b, 1, cin, 1, 1)
+        wt = sd['conv.weight'] / math.sqrt(cin * 9) * s
+        wt = wt * torch.rsqrt(wt.pow(2).sum([2, 3, 4]) + 1e-8).view(b, -1, 1, 1, 1)
+        out = F.conv_transpose2d(x.reshape(1, b * cin, h, h), wt.transpose(1, 2).reshape(b * cin, -1, 3, 3), stride=2, groups=b)
+        out = orc.upfirdn2d(out.view(b, -1, 2 * h + 1, 2 * h + 1), fir, pad=(1, 1))
+        return orc.fused_leaky_relu(out + sd['noise.weight'] * nz, sd['activate.bias'])
+
+    with torch.no_grad():
+        m.noise.weight.fill_(0.3)
+        m.activate.bias.copy_(T(rng.standard_normal(32, dtype=np.float32)))
+        for trial in range(2):
+            if trial == 1:                                    # perturb one tap: no longer an outer product
+                m.conv.blur.kernel[1, 2] += 0.05
+                assert m.conv.up_mode() == 1
+            sd = {k: v.cpu() for k, v in m.state_dict().items()}
+            ref = reference(sd, sd['conv.blur.kernel'])
+            y = m(x.cuda(), w.cuda(), noise=nz.cuda())
+            assert err(y, ref.numpy()) <= 1e-4 * max(1.0, float(ref.abs().max())), trial
+
+
+def test_single_pass_bf16_mode_reports_parity(pkg, monkeypatch):
+    """BASELINE config 5 precision (SGR_PRECISION=bf16: one bf16 MMA per product): parity is reported, not gated at 1e-3;
+    it must stay within plain-bf16 rounding of the fp32 result (5.7e-2 on a +-9 range)."""
+    size, cm = 64, 2
+    sd = orc.seeded_state_dict(size, cm, seed=3)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, 2, G.n_latent, seed=9)
+    with torch.no_grad():
+        ref = G([wplus.cuda()], input_is_latent=True)[0]
+        monkeypatch.setenv('SGR_PRECISION', 'bf16')
+        img = G([wplus.cuda()], input_is_latent=True)[0]
+    e = (img - ref).abs().max().item()
+    rng_ = ref.abs().max().item()
+    print('bf16 single-pass: max-abs %.3e on range %.2f' % (e, rng_))
+    assert 1e-5 < e <= 2e-2 * rng_

@@ -45,6 +45,7 @@ def run(B, only=None, reps=5):
         a.ksize, a.up, a.act, a.act_gain = 3, up, 1, 2 ** 0.5
         a.operand_format = a.out_format = 0
         a.column_tile = nt
+        a.single_pass = N.single_pass()
         a.x_c8, a.w_packed, a.demod, a.bias = N.ptr(xc8), N.ptr(packed), N.ptr(demod), N.ptr(bias)
         a.noise, a.noise_weight, a.s2, a.out_c8 = N.ptr(noise), N.ptr(nw), N.ptr(s2), N.ptr(out)
         if up == 2:
