@@ -94,6 +94,16 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes (read + write) of the conv GEMM launches of one step from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json, written by tools/ncu_summary.py); None if no capture has been summarised."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            return json.load(f)['conv_dram_bytes_per_step']
+    except Exception:
+        return None
+
+
 def conv_flops_per_frame():
     """Algorithmic 3x3 modconv FLOPs per frame, per styled layer."""
     from oracle import stylegan2_oracle as orc
@@ -295,22 +305,43 @@ def main():
             step_resident(i)
         torch.cuda.synchronize()
         buf = (ctypes.c_float * 8192)()
-        n = lib.sgr_profile_collect(buf, 8192)
+        tags = (ctypes.c_int * 8192)()
+        n = lib.sgr_profile_collect_tagged(buf, tags, 8192)
         lib.sgr_profile_enable(0)
-        per_step = n // prof_steps
+        gemm_ms = [buf[i] for i in range(n) if tags[i] == 0]
+        fin_ms = [buf[i] for i in range(n) if tags[i] == 1]
+        per_step = len(gemm_ms) // prof_steps
         fl = conv_flops_per_frame()
         assert per_step == len(fl), (per_step, len(fl))
-        dur = [sum(buf[s * per_step + l] for s in range(prof_steps)) / prof_steps for l in range(per_step)]   # ms
+        dur = [sum(gemm_ms[s * per_step + l] for s in range(prof_steps)) / prof_steps for l in range(per_step)]   # ms
         pk = peaks()
         total_ms = sum(dur)
         total_fl = sum(fl) * BATCH
         achieved = total_fl / (total_ms * 1e-3) / 1e12
-        issue_mult = [12 if l % 2 == 1 else 3 for l in range(per_step)]       # up layers: 4 phases x bf16x3
-        issued = sum(f * m for f, m in zip(fl, issue_mult)) * BATCH / (total_ms * 1e-3) / 1e12
-        roofline = {'bound': 'tensor', 'kernel': 'modconv_kernel (13 launches/step)', 'achieved': achieved,
-                    'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'], 'traffic': None,
+        issued = 3 * achieved                                      # bf16x3: 3 MMAs per product on every layer
+        # HBM-bound second pass of the upsampling layers: reads the fp32 parity planes, writes the hi/lo activations
+        fin_per_step = len(fin_ms) // prof_steps
+        fin_total = sum(fin_ms) / prof_steps
+        fin_bytes = 0
+        from oracle import stylegan2_oracle as orc
+        channels, log_size, _, _ = orc.synthesis_config(SIZE, CM)
+        for i in range(3, log_size + 1):
+            cout, h = channels[2 ** i], 2 ** (i - 1)
+            fin_bytes += BATCH * cout * (4 * (h + 1) ** 2 * 4 + (2 * h) ** 2 * 4)
+        roofline = {'bound': 'tensor',
+                    'kernel': 'tcgen05 conv kernels: modconv / modconv_halo / upconv_scatter (%d launches/step)' % per_step,
+                    'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
+                    'traffic': ncu_traffic_bytes(),
                     'issued_tflops': issued, 'issued_frac': issued / pk['bf16'], 'peak_source': pk['src'],
-                    'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps)}
+                    'note': 'achieved = algorithmic conv FLOPs (SURVEY 8d, 29.746 GFLOP/frame) / summed CUDA-event time of '
+                            'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
+                            'comparable to the bf16 dense peak',
+                    'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps),
+                    'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step)' % fin_per_step, 'bound': 'hbm',
+                                 'ms_per_step': fin_total, 'algorithmic_bytes': fin_bytes,
+                                 'achieved': fin_bytes / (fin_total * 1e-3) / 1e9 if fin_total > 0 else None,
+                                 'peak': pk['hbm'], 'unit': 'GB/s',
+                                 'frac': fin_bytes / (fin_total * 1e-3) / 1e9 / pk['hbm'] if fin_total > 0 else None}}
         layers = [{'layer': l, 'ms': round(d, 4), 'algo_tflops': round(f * BATCH / (d * 1e-3) / 1e12, 2)}
                   for l, (d, f) in enumerate(zip(dur, fl))]
 

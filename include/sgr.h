@@ -44,10 +44,13 @@ long long sgr_launch_count(void);
 void sgr_reset_launch_count(void);
 
 /* Per-launch timing of the modconv kernel (bench.py's roofline): while enabled, every sgr_modconv_forward records a
- * CUDA event pair on its stream around the launch.  sgr_profile_collect synchronises on the recorded events, writes up
+ * CUDA event pair on its stream around each of its launches.  sgr_profile_collect synchronises on the recorded events, writes up
  * to `cap` durations (milliseconds, launch order) and clears the list; returns the number of launches recorded. */
 void sgr_profile_enable(int on);
 int sgr_profile_collect(float* ms, int cap);
+/* same, also returning the kind of each timed launch: 0 = tensor-core convolution GEMM, 1 = FIR/epilogue pass of an
+ * up == 2 layer (HBM-bound) */
+int sgr_profile_collect_tagged(float* ms, int* tags, int cap);
 
 /* ---------------------------------------------------------------------------------------------------------
  * upfirdn2d: zero-insert upsample x`up`, pad (pad0 before / pad1 after, negative crops), true 2-D convolution

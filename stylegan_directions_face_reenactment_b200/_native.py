@@ -62,6 +62,7 @@ SIGNATURES = {
     'sgr_reset_launch_count': (None, []),
     'sgr_profile_enable': (None, [C.c_int]),
     'sgr_profile_collect': (C.c_int, [C.POINTER(C.c_float), C.c_int]),
+    'sgr_profile_collect_tagged': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
     'sgr_upfirdn2d': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 9 + [_fp]),
     'sgr_fused_bias_act': (C.c_int, [_fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                      C.c_float, _fp]),

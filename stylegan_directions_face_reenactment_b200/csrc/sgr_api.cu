@@ -30,15 +30,17 @@ bool check_launch(const char* what) {
 static bool g_prof_on = false;
 static const int kProfCap = 8192;
 static cudaEvent_t g_prof_ev[kProfCap][2];
+static int g_prof_tag[kProfCap];
 static int g_prof_made = 0, g_prof_n = 0;
 
-static bool prof_begin(cudaStream_t st) {
+static bool prof_begin(cudaStream_t st, int tag = 0) {
   if (!g_prof_on || g_prof_n >= kProfCap) return false;
   while (g_prof_made <= g_prof_n) {
     cudaEventCreate(&g_prof_ev[g_prof_made][0]);
     cudaEventCreate(&g_prof_ev[g_prof_made][1]);
     ++g_prof_made;
   }
+  g_prof_tag[g_prof_n] = tag;
   cudaEventRecord(g_prof_ev[g_prof_n][0], st);
   return true;
 }
@@ -236,24 +238,29 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   if (rc == 0 && args->up == 2) {
     const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
     const float comp = acc_comp_enabled() ? 1.16e-8f * (args->single_pass ? 1.f : 3.f) * static_cast<float>(args->cin / 16) : 0.f;
+    const bool prof2 = prof_begin(static_cast<cudaStream_t>(stream), 1);
     rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream));
+    if (prof2) prof_end(static_cast<cudaStream_t>(stream));
   }
   return rc;
 }
 
 void sgr_profile_enable(int on) { g_prof_on = on != 0; }
 
-int sgr_profile_collect(float* ms, int cap) {
+int sgr_profile_collect_tagged(float* ms, int* tags, int cap) {
   const int n = g_prof_n;
   for (int i = 0; i < n; ++i) {
     float t = 0.f;
     cudaEventSynchronize(g_prof_ev[i][1]);
     cudaEventElapsedTime(&t, g_prof_ev[i][0], g_prof_ev[i][1]);
     if (ms && i < cap) ms[i] = t;
+    if (tags && i < cap) tags[i] = g_prof_tag[i];
   }
   g_prof_n = 0;
   return n;
 }
+
+int sgr_profile_collect(float* ms, int cap) { return sgr_profile_collect_tagged(ms, nullptr, cap); }
 
 int sgr_style_affine(const float* latent, int latent_stride, int batch, const float* mod_weight, const float* mod_bias,
                      int cin, float* s_out, void* stream) {

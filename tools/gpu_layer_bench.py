@@ -63,9 +63,10 @@ def run(B, only=None, reps=5):
         e1.record()
         torch.cuda.synchronize()
         buf = (C.c_float * 64)()
-        n = lib.sgr_profile_collect(buf, 64)
+        tags = (C.c_int * 64)()
+        n = lib.sgr_profile_collect_tagged(buf, tags, 64)
         lib.sgr_profile_enable(0)
-        gemm = sum(buf[i] for i in range(n)) / n
+        gemm = sum(buf[i] for i in range(n) if tags[i] == 0) / reps
         total = e0.elapsed_time(e1) / reps
         fl = 2 * cin * cout * 9 * h * h * B
         print('%-26s gemm %.4f ms (%.0f algo TF/s)  call %.4f ms  [box %s]' % (name, gemm, fl / gemm / 1e9, total,
