@@ -82,7 +82,7 @@ __device__ __forceinline__ void split_pair_bf16(float v0, float v1, uint32_t& hi
 
 // ROWS: input rows walked by one warp (H % ROWS == 0, so the loop is uniform and the shuffles need no re-convergence code)
 template <int ROWS, int FMT, bool F32OUT>
-__global__ void __launch_bounds__(128, 5) up_finish_kernel(const UpFinishParams p) {
+__global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams p) {
   // sc[0..3] = gy (vertical taps, flipped), sc[4..7] = gx (horizontal taps, flipped, normalised by the tap sum)
   __shared__ float sc[8];
   if (threadIdx.x < 4) {
@@ -159,13 +159,29 @@ __global__ void __launch_bounds__(128, 5) up_finish_kernel(const UpFinishParams 
   F4 oe_0 = f4_load(t_oe, col_ok);
   F4 oo_0 = f4_load(t_oo, col_ok);
 
+  // software pipeline: the plane rows (and noise) of the NEXT iteration are requested before this iteration's math, so
+  // the HBM latency overlaps ~400 instructions of work instead of stalling the first FMA (61 % long-scoreboard stalls
+  // without it)
+  t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;        // row m0+1 <= H always exists
+  F4 ee_n = f4_load(t_ee, col_ok), eo_n = f4_load(t_eo, col_ok), oe_n = f4_load(t_oe, col_ok), oo_n = f4_load(t_oo, col_ok);
+  float2 nz_n[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  if (nz_ptr) {
+    nz_n[0] = __ldg(reinterpret_cast<const float2*>(nz_ptr));
+    nz_n[1] = __ldg(reinterpret_cast<const float2*>(nz_ptr + Wo));
+  }
 #pragma unroll 1
   for (int i = 0; i < ROWS; ++i) {
-    t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;      // row m+1 <= H always exists
-    const F4 ee_1 = f4_load(t_ee, col_ok);
-    const F4 eo_1 = f4_load(t_eo, col_ok);
-    const F4 oe_1 = f4_load(t_oe, col_ok);
-    const F4 oo_1 = f4_load(t_oo, col_ok);
+    const F4 ee_1 = ee_n, eo_1 = eo_n, oe_1 = oe_n, oo_1 = oo_n;
+    const float2 nz_c[2] = {nz_n[0], nz_n[1]};
+    if (i + 1 < ROWS) {
+      t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;    // row m+2 <= H inside the strip
+      ee_n = f4_load(t_ee, col_ok); eo_n = f4_load(t_eo, col_ok); oe_n = f4_load(t_oe, col_ok); oo_n = f4_load(t_oo, col_ok);
+      if (nz_ptr) {
+        nz_ptr += 2 * Wo;
+        nz_n[0] = __ldg(reinterpret_cast<const float2*>(nz_ptr));
+        nz_n[1] = __ldg(reinterpret_cast<const float2*>(nz_ptr + Wo));
+      }
+    }
     // vertical pass: T rows 2m-1 .. 2m+3 of the even (2n) and odd (2n+1) column
     F4 ve[2], vo[2];
     ve[0] = f4_fma(e3e, ee_1, f4_fma(e2o, oe_0, f4_fma(e1e, ee_0, f4_mul(e0o, oe_m1))));
@@ -185,10 +201,9 @@ __global__ void __launch_bounds__(128, 5) up_finish_kernel(const UpFinishParams 
       const F4 z1 = f4_fma(gx3, vo_r, f4_fma(gx2, ve_r, f4_fma(gx1, vo[py], f4_mul(gx0, ve[py]))));
       float2 nz0 = b01, nz1 = b01, nz2 = b23, nz3 = b23;          // (px0: ch01, px1: ch01, px0: ch23, px1: ch23)
       if (nz_ptr) {
-        const float2 nn = __ldg(reinterpret_cast<const float2*>(nz_ptr));
+        const float2 nn = nz_c[py];
         const float2 n0 = make_float2(nw * nn.x, nw * nn.x), n1 = make_float2(nw * nn.y, nw * nn.y);
         nz0 = __fadd2_rn(b01, n0); nz1 = __fadd2_rn(b01, n1); nz2 = __fadd2_rn(b23, n0); nz3 = __fadd2_rn(b23, n1);
-        nz_ptr += Wo;
       }
       // t = z * demod + noise + bias ; leaky relu
       float2 t0a = __ffma2_rn(z0.a, d01, nz0), t0b = __ffma2_rn(z0.b, d23, nz2);      // px 0: channels 01, 23
