@@ -193,49 +193,79 @@ __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ lat
 
 // ------------------------------------------------------------------------------------------------ demod + tables
 
-// One warp per (job, o, group of 8 samples): the wsq row (<= 512 inputs) stays in registers and is reused by the samples
-// of the group, four samples at a time as independent chains (one warp per (b, o) re-read every row once per sample:
-// 270 MB of L2 traffic at B = 32).
-constexpr int kTableBatchGroup = 8;
+// Demodulation + epilogue tables: d[b,o] = rsqrt(sum_i s[b,i]^2 wsq[o,i] + 1e-8) as a small GEMM per layer.
+// Block = (layer, 32 output channels, up to 32 samples): s^2 of the samples is staged once in shared memory; a warp owns
+// one output at a time, its lanes hold coalesced slices of the wsq row (cin <= 512: 16 registers) and accumulate all 32
+// samples in registers; a 31-shuffle reduce-scatter then leaves sample b's sum in lane b.
+// (One warp per (b, o) re-read each wsq row once per sample: 270 MB of L2 traffic at B = 32.)
+constexpr int kTableOutPerBlock = 16;
 constexpr int kTableMaxCinPerLane = 16;          // cin <= 512
 __global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int batch) {
+  extern __shared__ float s2[];                        // [32][cin]
   const TableJob& j = jobs.job[blockIdx.y];
+  const int o0 = blockIdx.x * kTableOutPerBlock;
+  if (o0 >= j.cout) return;
+  const int b0 = blockIdx.z * 32;
+  const int nb = min(32, batch - b0);
+  for (int idx = threadIdx.x; idx < 32 * j.cin; idx += blockDim.x) {
+    const int b = idx / j.cin, i = idx - b * j.cin;
+    const float v = b < nb ? __ldg(j.s + static_cast<size_t>(b0 + b) * j.cin + i) : 0.f;
+    s2[idx] = v * v;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (o >= j.cout) return;
-  const float* q = j.wsq + static_cast<size_t>(o) * j.cin;
-  float wq[kTableMaxCinPerLane];
-#pragma unroll
-  for (int t = 0; t < kTableMaxCinPerLane; ++t) wq[t] = lane + 32 * t < j.cin ? __ldg(q + lane + 32 * t) : 0.f;
-  const int b0 = blockIdx.z * kTableBatchGroup;
   const float kSqrt2 = 1.4142135623730951f;
 #pragma unroll 1
-  for (int bb = b0; bb < min(b0 + kTableBatchGroup, batch); bb += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int oo = warp; oo < kTableOutPerBlock / 2; oo += 8) {
+    // two outputs per pass share every s^2 read (the loop is shared-memory-load bound)
+    const int oa = o0 + oo, ob = oa + kTableOutPerBlock / 2;
+    if (oa >= j.cout) break;
+    const bool has_b = ob < j.cout;
+    const float* qa = j.wsq + static_cast<size_t>(oa) * j.cin;
+    const float* qb = j.wsq + static_cast<size_t>(has_b ? ob : oa) * j.cin;
+    float acc[32], bcc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = bcc[b] = 0.f;
 #pragma unroll
     for (int t = 0; t < kTableMaxCinPerLane; ++t) {
-      if (32 * t < j.cin) {                       // warp-uniform
+      if (32 * t < j.cin) {                          // warp-uniform
+        const float wa = __ldg(qa + lane + 32 * t), wb = __ldg(qb + lane + 32 * t);
+        const float* col = s2 + lane + 32 * t;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int b = min(bb + u, batch - 1);
-          const float sv = lane + 32 * t < j.cin ? __ldg(j.s + static_cast<size_t>(b) * j.cin + lane + 32 * t) : 0.f;
-          acc[u] = fmaf(sv * sv, wq[t], acc[u]);
+        for (int b = 0; b < 32; ++b) {
+          const float sv = col[b * j.cin];
+          acc[b] = fmaf(sv, wa, acc[b]);
+          bcc[b] = fmaf(sv, wb, bcc[b]);
         }
       }
     }
+    // reduce-scatter over the lanes: after the step with offset `off` a lane keeps the half of the samples whose bit
+    // `off` equals its own, so lane b ends with the total of sample b in acc[0] / bcc[0]
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+      const bool up = (lane & off) != 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
-    if (lane < 4 && bb + lane < batch) {
-      const int b = bb + lane;
-      const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
-      j.demod[static_cast<size_t>(b) * j.cout + o] = rsqrtf(a + 1e-8f);
-      if (j.s_next) j.s2[static_cast<size_t>(b) * j.cout + o] = kSqrt2 * __ldg(j.s_next + static_cast<size_t>(b) * j.cout + o);
-      if (j.s_rgb) {
-        const float sr = kSqrt2 * __ldg(j.s_rgb + static_cast<size_t>(b) * j.cout + o) * rsqrtf(static_cast<float>(j.cout));
-        for (int c = 0; c < 3; ++c)
-          j.rgb_coef[(static_cast<size_t>(b) * 3 + c) * j.cout + o] = sr * __ldg(j.w_rgb + c * j.cout + o);
+      for (int k = 0; k < n / 2; ++k) {
+        const float send = up ? acc[k] : acc[k + n / 2], keep = up ? acc[k + n / 2] : acc[k];
+        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        const float send2 = up ? bcc[k] : bcc[k + n / 2], keep2 = up ? bcc[k + n / 2] : bcc[k];
+        bcc[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+      }
+    }
+    if (lane < nb) {
+      const int b = b0 + lane;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !has_b) break;
+        const int o = h ? ob : oa;
+        const float a = h ? bcc[0] : acc[0];
+        j.demod[static_cast<size_t>(b) * j.cout + o] = rsqrtf(a + 1e-8f);
+        if (j.s_next) j.s2[static_cast<size_t>(b) * j.cout + o] = kSqrt2 * __ldg(j.s_next + static_cast<size_t>(b) * j.cout + o);
+        if (j.s_rgb) {
+          const float sr = kSqrt2 * __ldg(j.s_rgb + static_cast<size_t>(b) * j.cout + o) * rsqrtf(static_cast<float>(j.cout));
+          for (int c = 0; c < 3; ++c)
+            j.rgb_coef[(static_cast<size_t>(b) * 3 + c) * j.cout + o] = sr * __ldg(j.w_rgb + c * j.cout + o);
+        }
       }
     }
   }
@@ -369,13 +399,25 @@ int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_str
 int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st) {
   int cmax = 0;
   for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cout ? cmax : jobs.job[i].cout;
-  for (int i = 0; i < jobs.n; ++i)
-    if (jobs.job[i].cin > 32 * kTableMaxCinPerLane) {
-      set_error("table_kernel: cin %d > %d unsupported", jobs.job[i].cin, 32 * kTableMaxCinPerLane);
+  int cin_max = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    cin_max = cin_max > jobs.job[i].cin ? cin_max : jobs.job[i].cin;
+    if (jobs.job[i].cin % 32 != 0 || jobs.job[i].cin > 32 * kTableMaxCinPerLane) {
+      set_error("table_kernel: cin %d must be a multiple of 32 and <= %d", jobs.job[i].cin, 32 * kTableMaxCinPerLane);
       return 1;
     }
-  dim3 grid((cmax + 7) / 8, jobs.n, (batch + kTableBatchGroup - 1) / kTableBatchGroup);
-  table_kernel<<<grid, 256, 0, st>>>(jobs, batch);
+  }
+  const int smem = 32 * cin_max * 4;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    if (cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("table_kernel: cin %d needs %d bytes of shared memory", cin_max, smem);
+      return 1;
+    }
+    configured_smem = smem;
+  }
+  dim3 grid((cmax + kTableOutPerBlock - 1) / kTableOutPerBlock, jobs.n, (batch + 31) / 32);
+  table_kernel<<<grid, 256, smem, st>>>(jobs, batch);
   count_launch();
   return check_launch("table_kernel") ? 0 : 1;
 }

@@ -1,0 +1,82 @@
+"""Summarises ncu captures of bench.py into the tracked files under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/launches.csv  profiles/r1_launches_summary.md
+    python tools/ncu_summary.py full     gpurun_out/prof.ncu-rep  profiles/r1_conv_ncu.md profiles/r1_traffic.json
+
+`launches`: CSV of `ncu --metrics gpu__time_duration.sum --clock-control none --csv` -> per-kernel totals and shares.
+`full`: .ncu-rep of `ncu --set full -k regex:"modconv|upconv|up_finish"` over exactly one step -> per-launch table
+(duration, grid, tensor-pipe %, L2 %, DRAM %, DRAM bytes) and the DRAM traffic of the conv GEMMs per step (bench.py's
+roofline.traffic)."""
+import collections
+import csv
+import json
+import subprocess
+import sys
+
+
+def launches(src, dst, cmd_note=''):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ki]
+        t = float(r[vi].replace(',', '')) / 1000.0            # ns -> us
+        n, tot = agg.get(name, (0, 0.0))
+        agg[name] = (n + 1, tot + t)
+    total = sum(t for _, t in agg.values())
+    with open(dst, 'w') as f:
+        f.write('# ncu launch list of `python bench.py --steps 2 --warmup 3 --cpu-baseline 0`\n\n')
+        f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file '
+                'gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --cpu-baseline 0` (B200; cold-cache, '
+                'serialised launches: compare shares, not absolutes). %s\n\n' % cmd_note)
+        f.write('| kernel | launches | total us | share |\n|---|---|---|---|\n')
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write('| `%s` | %d | %.1f | %.1f%% |\n' % (name[:90], n, t, 100 * t / total))
+    print('wrote', dst)
+
+
+def full(src, dst_md, dst_json):
+    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, data = rows[0], rows[2:]
+    cols = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'us'), ('launch__grid_size', 'grid'),
+            ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %'),
+            ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %'),
+            ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 %'),
+            ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %'),
+            ('dram__bytes_read.sum', 'DRAM rd MB'), ('dram__bytes_write.sum', 'DRAM wr MB')]
+    idx = [hdr.index(c) for c, _ in cols]
+    conv_bytes = 0.0
+    fin_bytes = 0.0
+    lines = []
+    for r in data:
+        vals = [r[i] for i in idx]
+        name = vals[0].replace('void sgr::', '').replace('sgr::', '').split('(')[0]
+        rd, wr = float(vals[7].replace(',', '')), float(vals[8].replace(',', ''))
+        if 'up_finish' in name:
+            fin_bytes += (rd + wr) * 1e6
+        else:
+            conv_bytes += (rd + wr) * 1e6
+        lines.append('| `%s` | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (
+            name, vals[1], vals[2], float(vals[3]), float(vals[4]), float(vals[5]), float(vals[6]), rd, wr))
+    with open(dst_md, 'w') as f:
+        f.write('# `ncu --set full` of the conv GEMM + FIR-pass launches of one step (B=32, 256^2, cm=1)\n\n')
+        f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:"modconv|upconv|up_finish" '
+                '-s <launches of 3 warm-up steps> -c <launches of one step> -o gpurun_out/prof python bench.py --steps 2 '
+                '--warmup 3 --cpu-baseline 0` (the .ncu-rep stays out of git; this table is `ncu -i ... --page raw --csv` '
+                'filtered by tools/ncu_summary.py).  Durations under ncu are cold-cache and serialised.\n\n')
+        f.write('| ' + ' | '.join(n for _, n in cols) + ' |\n|' + '---|' * len(cols) + '\n')
+        f.write('\n'.join(lines) + '\n\n')
+        f.write('DRAM traffic per step: conv GEMMs %.1f MB, FIR pass %.1f MB.\n' % (conv_bytes / 1e6, fin_bytes / 1e6))
+    with open(dst_json, 'w') as f:
+        json.dump({'conv_dram_bytes_per_step': conv_bytes, 'up_finish_dram_bytes_per_step': fin_bytes,
+                   'source': 'ncu --set full, one step of bench.py (B=32, 256^2, cm=1); see ' + dst_md}, f, indent=1)
+    print('wrote', dst_md, dst_json)
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'launches':
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4])
