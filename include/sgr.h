@@ -134,6 +134,9 @@ typedef struct sgr_conv_args {
   float* rgb_partial;     /* [cout/column_tile][B,3,h_out,w_out], fully overwritten */
   float* t_scratch;       /* up == 2: sgr_up_scratch_bytes() of scratch */
   const float* fir;       /* up == 2: blur.kernel [4,4]; must be an outer product (rank 1), as make_kernel builds it */
+  void* splitk_scratch;   /* optional: >= splitk_scratch_bytes of scratch enabling split-K on layers with fewer output
+                             tiles than SMs (4x4 .. 16x16 grids, small batches); NULL = never split */
+  size_t splitk_scratch_bytes;
   int single_pass;        /* 0: split-precision products (3 MMAs, fp32 parity); 1: hi x hi only = plain bf16/fp16
                              tensor-core precision with fp32 accumulation (BASELINE config 5), 1 MMA per product */
 } sgr_conv_args;

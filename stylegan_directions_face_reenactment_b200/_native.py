@@ -35,7 +35,8 @@ class ConvArgs(C.Structure):
                 ('ksize', C.c_int), ('up', C.c_int), ('act', C.c_int), ('act_gain', C.c_float), ('operand_format', C.c_int), ('column_tile', C.c_int), ('out_format', C.c_int),
                 ('x_c8', _fp), ('w_packed', _fp), ('demod', _fp), ('bias', _fp), ('noise', _fp),
                 ('noise_batch_stride', C.c_longlong), ('noise_weight', _fp), ('s2', _fp), ('out_c8', _fp),
-                ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_partial', _fp), ('t_scratch', _fp), ('fir', _fp), ('single_pass', C.c_int)]
+                ('out_f32', _fp), ('rgb_coef', _fp), ('rgb_partial', _fp), ('t_scratch', _fp), ('fir', _fp), ('splitk_scratch', _fp), ('splitk_scratch_bytes', C.c_size_t),
+                ('single_pass', C.c_int)]
 
 
 class StyledLayer(C.Structure):

@@ -221,6 +221,7 @@ struct BwdPlan {
   size_t acc_begin, acc_end;
   size_t grgb_off[SGR_MAX_RGB];
   size_t gz_off, gx_off[2];
+  size_t splitk_off;
   size_t total;
 };
 
@@ -269,6 +270,7 @@ static int plan_backward(const sgr_synthesis* net, int batch, BwdPlan* pl) {
   for (int i = 0; i < 2; ++i) {
     pl->gx_off[i] = off; off = align_up(off + max_in * 4, 256);
   }
+  pl->splitk_off = off; off = align_up(off + kSplitKScratchBytes, 256);
   pl->total = off;
   return 0;
 }
@@ -409,6 +411,8 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     a.x_c8 = ws + pl.gz_off;
     a.w_packed = Ly.w_packed_t;
     a.out_f32 = F(pl.gx_off[gx_cur]);
+    a.splitk_scratch = ws + pl.splitk_off;
+    a.splitk_scratch_bytes = kSplitKScratchBytes;
     if (sgr_modconv_forward(&a, stream)) return 1;
     gx_next = F(pl.gx_off[gx_cur]);
     gx_cur = 1 - gx_cur;

@@ -87,22 +87,25 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int out_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice of channel blocks)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t ai = 0, bi = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile / p.m_tiles;
-        int m = tile - n_tile * p.m_tiles;
+        const int ks = tile % p.ksplit, otile = tile / p.ksplit;
+        const int n_tile = otile / p.m_tiles;
+        int m = otile - n_tile * p.m_tiles;
         const int tx = m % p.tiles_x;
         m /= p.tiles_x;
         const int ty = m % p.tiles_y;
         const int b = m / p.tiles_y;
         const int x0 = tx * Cfg::kTileW - 1, y0 = ty * Cfg::kTileH - 1;
         const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(n_tile) * 9 * p.kchunks * (NT * 64);
-        for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+        const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
           mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
           mbar_expect_tx(&a_full[as], Cfg::kABytes);
@@ -131,7 +134,9 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * Cfg::kAccCols);
-        for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+        const int ks = tile % p.ksplit;
+        const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
           mbar_wait(&a_full[as], (ai / AS) & 1);
           tc_fence_after();
@@ -152,13 +157,13 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
                 const uint64_t a_lo = umma_desc(a_off + kAPlane, kALbo, kASbo);
                 const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
                 if (p.single) {
-                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc, (kb | tap | j) != 0);
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc, (kb > kb0 || (tap | j) != 0));
                 } else if (Cfg::kConcat) {
-                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, (kb | tap | j) != 0);   // hi*hi | hi*lo
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, (kb > kb0 || (tap | j) != 0));   // hi*hi | hi*lo
                   umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, idesc, 1);                         // lo*hi
                 } else {
                   const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
-                  umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb | tap | j) != 0);
+                  umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb > kb0 || (tap | j) != 0));
                   umma_bf16(d_tmem + mt * NT, a_hi, b_lo, idesc, 1);
                   umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
                 }
@@ -179,8 +184,10 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
     const size_t plane_stride = static_cast<size_t>(p.B) * p.cout * p.Hout * p.Wout;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int n_tile = tile / p.m_tiles;
-      int m = tile - n_tile * p.m_tiles;
+      const int ks = tile % p.ksplit, otile = tile / p.ksplit;
+      const int n_tile = otile / p.m_tiles;
+      int m = otile - n_tile * p.m_tiles;
+      const int m_tile = m;
       const int tx = m % p.tiles_x;
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
@@ -208,9 +215,17 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
           } else {
             tmem_ld_wait();
           }
+          if (p.ksplit > 1) {          // raw partial sums of this K slice -> kpart[ks][n_tile][m_tile * MT + mt][row][NT]
+            float4* dst = reinterpret_cast<float4*>(
+                p.kpart + (((static_cast<size_t>(ks) * p.n_tiles + n_tile) * p.m_tiles + m_tile) * MT + mt) * (kTileM * NT) +
+                static_cast<size_t>(r) * NT + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            continue;
+          }
           if (valid) epilogue_32cols(p, v, n_tile * NT + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
         }
-        if (valid && p.rgb_coef) rgb_store(p, n_tile, b, y, x, rgb0, rgb1, rgb2);
+        if (valid && p.rgb_coef && p.ksplit == 1) rgb_store(p, n_tile, b, y, x, rgb0, rgb1, rgb2);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -239,7 +254,7 @@ static int launch_halo(const ConvKernelParams& p, const CUtensorMap& tmap, int s
     }
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   modconv_halo_kernel<NT, MT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, p);
   count_launch();
   return check_launch("modconv_halo_kernel") ? 0 : 1;
@@ -267,15 +282,21 @@ int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t
   p.tiles_b = a->batch;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   p.n_tiles = a->cout / nt;
+  p.halo_mt = mt;
+  p.nt = nt;
+  set_ksplit(&p, choose_ksplit(a, p.m_tiles * p.n_tiles, p.kchunks, 2, static_cast<size_t>(mt) * kTileM * nt * 4));
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw + 2, p.bh + 2, 1)) return 1;
+  int rc;
   switch (nt) {
-    case 256: return launch_halo<256, 1>(p, tmap, sms, stream);
-    case 128: return launch_halo<128, 2>(p, tmap, sms, stream);
-    case 64: return launch_halo<64, 2>(p, tmap, sms, stream);
-    case 32: return launch_halo<32, 2>(p, tmap, sms, stream);
+    case 256: rc = launch_halo<256, 1>(p, tmap, sms, stream); break;
+    case 128: rc = launch_halo<128, 2>(p, tmap, sms, stream); break;
+    case 64: rc = launch_halo<64, 2>(p, tmap, sms, stream); break;
+    case 32: rc = launch_halo<32, 2>(p, tmap, sms, stream); break;
     default: set_error("modconv_halo: unsupported column tile %d", nt); return 1;
   }
+  if (rc == 0 && p.ksplit > 1) rc = splitk_finish_launch(p, stream);
+  return rc;
 }
 
 }  // namespace sgr

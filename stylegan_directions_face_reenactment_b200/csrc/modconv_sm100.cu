@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int out_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice); slice fastest
   const int k_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
@@ -102,25 +103,24 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+        const int ks = tile % p.ksplit;
+        const TileCoord tc = decode_tile(p, tile / p.ksplit);
         const int x0 = tc.tx * p.bw, y0 = tc.ty * p.bh, b0 = tc.tb * p.bb;
         const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
-        {
-          const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
-            for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-              const uint32_t s = it % S;
-              const uint32_t ph = (it / S) & 1;
-              mbar_wait(&empty[s], ph ^ 1);
-              uint8_t* sa = stage_base + s * Cfg::kStageBytes;
-              mbar_expect_tx(&full[s], a_bytes + Cfg::kBBytes);
-              tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
-              bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(tap * p.kchunks + kc) * (NT * 64), Cfg::kBBytes,
-                       &full[s]);
-            }
-          }
+        const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
+        const int k0 = ks * k_iters / p.ksplit, k1 = (ks + 1) * k_iters / p.ksplit;
+        int tap = k0 / p.kchunks, kc = k0 - tap * p.kchunks;
+        for (int k = k0; k < k1; ++k, ++it) {
+          const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
+          const uint32_t s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = stage_base + s * Cfg::kStageBytes;
+          mbar_expect_tx(&full[s], a_bytes + Cfg::kBBytes);
+          tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
+          bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(k) * (NT * 64), Cfg::kBBytes, &full[s]);
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
         }
       }
     }
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * NT;
-        for (int k = 0; k < k_iters; ++k, ++it) {
+        const int ks = tile % p.ksplit;
+        const int k0 = ks * k_iters / p.ksplit, k1 = (ks + 1) * k_iters / p.ksplit;
+        for (int k = k0; k < k1; ++k, ++it) {
           constexpr uint32_t coloff = 0;
           const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
           // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64, see pack_weight_kernel)
@@ -153,11 +155,11 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
             const uint64_t b_hi = umma_desc(b_addr + j * 2 * b_lbo, b_lbo, 128);
             const uint64_t b_lo = umma_desc(b_addr + b_plane + j * 2 * b_lbo, b_lbo, 128);
             if (!p.single) {
-              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, (k | j) != 0);
+              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, k > k0 || j != 0);
               umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc, 1);
               umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, 1);
             } else {
-              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, (k | j) != 0);
+              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, k > k0 || j != 0);
             }
           }
           umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
     const size_t plane_stride = static_cast<size_t>(p.B) * p.cout * p.Hout * p.Wout;   // elements per C8 plane
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const TileCoord tc = decode_tile(p, tile);
+      const int ks = tile % p.ksplit, otile = tile / p.ksplit;
+      const TileCoord tc = decode_tile(p, otile);
       const int b = tc.tb * p.bb + bl;
       const int y = tc.ty * p.bh + yy;
       const int x = tc.tx * p.bw + xx;
@@ -190,11 +193,17 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * NT + c, v);
         tmem_ld_wait();
+        if (p.ksplit > 1) {            // raw partial sums of this K slice (splitk_finish_kernel adds and finishes)
+          float4* dst = reinterpret_cast<float4*>(p.kpart + ((static_cast<size_t>(ks) * out_tiles + otile) * kTileM + r) * NT + c);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          continue;
+        }
         if (valid) epilogue_32cols(p, v, tc.n_tile * NT + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);     // 128 arrivals release the accumulator buffer
-      if (valid && p.rgb_coef) rgb_store(p, tc.n_tile, b, y, x, rgb0, rgb1, rgb2);
+      if (valid && p.rgb_coef && p.ksplit == 1) rgb_store(p, tc.n_tile, b, y, x, rgb0, rgb1, rgb2);
     }
   }
 
@@ -234,7 +243,7 @@ static int launch_nt(const ConvKernelParams& p, const CUtensorMap& tmap, cudaStr
     set_error("modconv: no CUDA device");
     return 1;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(total, sms);
   modconv_kernel<NT><<<grid, 256, ConvCfg<NT>::kSmemBytes, stream>>>(tmap, p);
   count_launch();
@@ -297,6 +306,25 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
 bool acc_comp_enabled() {
   static const bool comp = [] { const char* e = getenv("SGR_ACC_COMP"); return !(e && e[0] == '0'); }();
   return comp;
+}
+
+// acc_scale for a K range cut into `ksplit` slices: each slice's accumulation chain is 1/ksplit as long
+void set_ksplit(ConvKernelParams* p, int ksplit) {
+  p->ksplit = ksplit < 1 ? 1 : ksplit;
+  p->acc_scale = p->acc_base * (1.f + 1.16e-8f * p->acc_mmas / static_cast<float>(p->ksplit));
+}
+
+// Split-K slices: enough to occupy the SMs when a layer has few output tiles, each slice keeping at least
+// `min_units_per_slice` K units; 1 (off) without scratch or when the tiles already fill the machine.
+int choose_ksplit(const sgr_conv_args* a, int tiles, int k_units, int min_units_per_slice, size_t tile_bytes) {
+  static const bool off = [] { const char* e = getenv("SGR_SPLITK"); return e && e[0] == '0'; }();
+  if (off || !a->splitk_scratch || tiles <= 0) return 1;
+  const int sms = num_sms();
+  if (sms <= 0 || 2 * tiles > sms) return 1;
+  int s = std::min(16, sms / tiles);
+  s = std::min(s, k_units / min_units_per_slice);
+  while (s > 1 && static_cast<size_t>(s) * tiles * tile_bytes > a->splitk_scratch_bytes) --s;
+  return s < 2 ? 1 : s;
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -441,14 +469,20 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   }
   p->fmt = a->operand_format;
   p->single = a->single_pass ? 1 : 0;
-  p->acc_scale = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
+  p->acc_base = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
+  p->acc_scale = p->acc_base;
+  p->ksplit = 1;
+  p->halo_mt = 0;
+  p->nt = *nt;
+  p->kpart = static_cast<float*>(a->splitk_scratch);
   // The tensor core's fp32 accumulate truncates: measured on B200 the result shrinks by ~1.16e-8 per MMA accumulated into
   // the same TMEM cell (tools/gpu_debug.py "mean signed rel err": -1.0e-5 at 864 MMAs, -1.6e-6 at 108).  Undo the mean.
   const bool comp = acc_comp_enabled();
   // (scatter up-conv: the parity planes see 4/2/2/1 taps; 9/4 on average over the 4 planes feeding each output)
   const float per_product = a->single_pass ? 1.f : 3.f;
   const float mmas = a->up == 2 ? per_product * 2.25f * (a->cin / 16) : per_product * a->ksize * a->ksize * (a->cin / 16);
-  if (comp) p->acc_scale *= 1.f + 1.16e-8f * mmas;
+  p->acc_mmas = comp ? mmas : 0.f;
+  set_ksplit(p, 1);
   p->out_fmt = a->out_format;
   p->out_scale = act_scale(a->out_format);
   p->wpacked = static_cast<const __nv_bfloat16*>(a->w_packed);

@@ -68,6 +68,7 @@ struct SynthPlan {
   size_t rgbacc_off[SGR_MAX_RGB];
   int rgb_slots[SGR_MAX_RGB];
   size_t t_off;
+  size_t splitk_off;
   size_t skip_off[2];
   size_t act_off[2];
   size_t total;
@@ -113,6 +114,7 @@ static int plan_synthesis(const sgr_synthesis* net, int batch, SynthPlan* pl) {
       if (e > max_t) max_t = e;
     }
   pl->t_off = off; off = align_up(off + max_t, 256);
+  pl->splitk_off = off; off = align_up(off + kSplitKScratchBytes, 256);
   const size_t S = static_cast<size_t>(net->size);
   for (int i = 0; i < 2; ++i) {
     pl->skip_off[i] = off; off = align_up(off + B * 3 * S * S * 4, 256);
@@ -231,9 +233,12 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   }
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
+  if (args->up != 2)
+    set_ksplit(&p, choose_ksplit(args, p.m_tiles * p.n_tiles, p.ntaps * p.kchunks, 8, static_cast<size_t>(kTileM) * nt * 4));
   const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
   rc = args->up == 2 ? launch_upconv_scatter(p, tmap, nt, static_cast<cudaStream_t>(stream))
                      : launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
+  if (rc == 0 && p.ksplit > 1) rc = splitk_finish_launch(p, static_cast<cudaStream_t>(stream));
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
   if (rc == 0 && args->up == 2) {
     const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
@@ -369,6 +374,8 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
     a.act_gain = 1.4142135623730951f;
     a.operand_format = net->format;
     a.single_pass = net->single_pass;
+    a.splitk_scratch = ws + pl.splitk_off;
+    a.splitk_scratch_bytes = kSplitKScratchBytes;
     a.column_tile = L.column_tile;
     a.out_format = net->format;
     a.x_c8 = ws + pl.act_off[cur];

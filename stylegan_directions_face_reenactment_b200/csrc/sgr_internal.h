@@ -64,7 +64,15 @@ struct ConvKernelParams {
   float* out_f32;
   const float* rgb_coef;
   float* rgb_part;              // [n_tiles][B,3,H,W] partial ToRGB sums, one slot per column tile
-  float* t_out;                 // mode 2: [B][4][cout/8][H][W][8] fp32 parity planes (H, W = grid dims above)
+  float* t_out;                 // mode 2: [B][4][cout/4][H][W][4] fp32 parity planes (H, W = grid dims above)
+  // split-K (small pixel grids / small batches: fewer tiles than SMs): the K range of a tile is cut into `ksplit` slices
+  // run by different CTAs; raw fp32 partials go to kpart[ks][n_tile][m_tile * sub + s][128][NT] and
+  // splitk_finish_kernel adds them in slice order (deterministic) and applies the fused epilogue
+  int ksplit;
+  int halo_mt;                  // 0: modconv_kernel row -> pixel mapping; 1, 2: modconv_halo_kernel sub-tiles per tile
+  int nt;
+  float* kpart;
+  float acc_base, acc_mmas;     // acc_scale = acc_base * (1 + 1.16e-8 * acc_mmas / ksplit)
 };
 
 // modconv_sm100.cu
@@ -77,6 +85,11 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
 int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // modconv_halo_sm100.cu: resident-halo variant for plain 3x3 layers of at least 16x16 pixels
 bool halo_eligible(const sgr_conv_args* a);
+// split-K: slices for a layer with `tiles` output tiles and `k_units` K units (0/1 = off); finish pass
+constexpr size_t kSplitKScratchBytes = 160u * 128u * 1024u;      // >= 148 CTA tiles x 128 rows x 256 columns x 4 B
+int choose_ksplit(const sgr_conv_args* a, int tiles, int k_units, int min_units_per_slice, size_t tile_bytes);
+void set_ksplit(ConvKernelParams* p, int ksplit);
+int splitk_finish_launch(const ConvKernelParams& p, cudaStream_t stream);
 int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream);
 
 // prep_kernels.cu

@@ -1,0 +1,72 @@
+// Second pass of a split-K convolution (modconv_sm100.cu / modconv_halo_sm100.cu with p.ksplit > 1): adds the fp32
+// partial accumulators of the K slices in slice order (deterministic) and applies the same fused epilogue
+// (demodulation, NoiseInjection, FusedLeakyReLU, next style + hi/lo split, ToRGB partials: modconv_epilogue.cuh).
+// Used on the layers whose pixel grid yields fewer output tiles than SMs (4x4 .. 16x16, or any layer at batch 1-4).
+// One thread per tile row (pixel), 32 columns at a time: 128 contiguous bytes per slice.
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+#include "modconv_epilogue.cuh"
+
+namespace sgr {
+
+__global__ void __launch_bounds__(128) splitk_finish_kernel(const ConvKernelParams p) {
+  const int r = threadIdx.x;
+  const int sub_tiles = p.halo_mt > 0 ? p.halo_mt : 1;
+  const int msub = blockIdx.x;                       // m_tile * sub_tiles + sub
+  const int m_tile = msub / sub_tiles, sub = msub - m_tile * sub_tiles;
+  const int n_tile = blockIdx.y;
+  int m = m_tile;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  const int tb = m / p.tiles_y;
+  int b, y, x;
+  bool valid;
+  if (p.halo_mt > 0) {                               // 8x16-pixel sub-tiles, one sample per tile
+    b = tb;
+    y = ty * 16 + (r >> 3);
+    x = tx * (8 * p.halo_mt) + sub * 8 + (r & 7);
+    valid = y < p.H && x < p.W;
+  } else {                                           // dense (bw, bh, bb) box
+    const int xx = r % p.bw, yy = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
+    b = tb * p.bb + bl;
+    y = ty * p.bh + yy;
+    x = tx * p.bw + xx;
+    valid = r < p.rows && b < p.B && y < p.H && x < p.W;
+  }
+  if (!valid) return;
+  const int nt = p.nt;
+  const size_t slice_stride = static_cast<size_t>(p.n_tiles) * p.m_tiles * sub_tiles * kTileM * nt;
+  const float* src = p.kpart + ((static_cast<size_t>(n_tile) * p.m_tiles * sub_tiles + msub) * kTileM + r) * nt;
+  const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+  const size_t plane_stride = static_cast<size_t>(p.B) * p.cout * p.Hout * p.Wout;
+  float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+  for (int c = 0; c < nt; c += 32) {
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(src + c + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    for (int ks = 1; ks < p.ksplit; ++ks) {
+      const float* sp = src + ks * slice_stride + c;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sp + 4 * q);
+        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      }
+    }
+    epilogue_32cols(p, v, n_tile * nt + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
+  }
+  if (p.rgb_coef) rgb_store(p, n_tile, b, y, x, rgb0, rgb1, rgb2);
+}
+
+int splitk_finish_launch(const ConvKernelParams& p, cudaStream_t stream) {
+  const int sub_tiles = p.halo_mt > 0 ? p.halo_mt : 1;
+  dim3 grid(p.m_tiles * sub_tiles, p.n_tiles);
+  splitk_finish_kernel<<<grid, 128, 0, stream>>>(p);
+  count_launch();
+  return check_launch("splitk_finish_kernel") ? 0 : 1;
+}
+
+}  // namespace sgr
