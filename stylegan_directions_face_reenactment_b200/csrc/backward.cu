@@ -32,6 +32,7 @@ struct BwdActParams {
   long long noise_bstride;
   const float* noise_w;
   __nv_bfloat16* out_c8;  // gz planes or NULL
+  float* out_gz4;         // gz as fp32 [B][C/4][H][W][4] (scatter-form up layers: input of up_bwd_prepare_kernel) or NULL
   int s2d;
   int act;                // 0: constant-input pseudo layer (only the ds reduction)
   float* ds_next;         // [B,C] += sum_p a * gx
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
     }
   }
   const float rs = rsqrtf(static_cast<float>(p.C));
-  __nv_bfloat16 hi[4][8], lo[4][8];
+  float gzv[4][8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = c0 + e;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
           const float gt = ga * (pos ? kSqrt2 : 0.2f * kSqrt2);
           const float t = pos ? a * kInvSqrt2 : a * (5.f * kInvSqrt2);
           qa = fmaf(gt, t - nz[j] - bi, qa);
-          split_bf16(gt * d, hi[j][e], lo[j][e]);
+          gzv[j][e] = gt * d;
         }
       }
     }
@@ -122,6 +123,15 @@ __global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
       if (p.ds_next && p.gx) atomicAdd(p.ds_next + o, dsn);
       if (p.act) atomicAdd(p.q + o, qa);
       if (p.grgb) atomicAdd(p.ds_rgb + o, dsr);
+    }
+  }
+  if (valid && p.out_gz4 && p.act) {
+    const int y = pix / p.W, x = pix % p.W;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float4* dst = reinterpret_cast<float4*>(p.out_gz4 + (((static_cast<size_t>(b) * (p.C / 4) + blockIdx.y * 2 + g) * p.H + y) * p.W + x) * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = make_float4(gzv[j][4 * g], gzv[j][4 * g + 1], gzv[j][4 * g + 2], gzv[j][4 * g + 3]);
     }
   }
   if (valid && p.out_c8 && p.act) {
@@ -139,15 +149,82 @@ __global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
         off = ((static_cast<size_t>(b) * (4 * chunks) + phase * chunks + blockIdx.y) * H2 + (y >> 1)) * W2 + ((x + j) >> 1);
         plane = static_cast<size_t>(p.B) * chunks * HW;      // 4*chunks * H2*W2 == chunks * HW
       }
-      uint4 h, l;
-      h.x = pack_bf16x2(hi[j][0], hi[j][1]); h.y = pack_bf16x2(hi[j][2], hi[j][3]);
-      h.z = pack_bf16x2(hi[j][4], hi[j][5]); h.w = pack_bf16x2(hi[j][6], hi[j][7]);
-      l.x = pack_bf16x2(lo[j][0], lo[j][1]); l.y = pack_bf16x2(lo[j][2], lo[j][3]);
-      l.z = pack_bf16x2(lo[j][4], lo[j][5]); l.w = pack_bf16x2(lo[j][6], lo[j][7]);
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split2(gzv[j][2 * e], gzv[j][2 * e + 1], kFmtBF16, hp[e], lp[e]);
       uint4* o4 = reinterpret_cast<uint4*>(p.out_c8);
-      o4[off] = h;
-      o4[plane + off] = l;
+      o4[off] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      o4[plane + off] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
+  }
+}
+
+// Scatter-form up layers, backward: G = FIR^T(gz) on the (2H+1)^2 grid of conv_transpose2d outputs, split into its four
+// parity planes [ee|eo|oe|oo] on the (H+1) x (W+1) grid and written as the bf16 hi/lo operand (4*C channels, plane-major)
+// of the 9-tap gather GEMM (sgr_conv_args.up == 3).  Adjoint of up_finish_kernel's FIR (upfirdn2d backward,
+// op/upfirdn2d.py:112-117): G[u][v] = sum_{a,b} fir[3-a][3-b] gz[u-a+1][v-b+1].
+struct UpBwdPrepParams {
+  int B, C, H, W;            // H, W = INPUT resolution of the up layer; gz is [B][C/4][2H][2W][4]
+  const float* gz;
+  const float* fir;          // [4][4] blur.kernel
+  __nv_bfloat16* planes;     // [2][B][4*C/8][H+1][W+1][8]
+};
+
+__global__ void __launch_bounds__(128) up_bwd_prepare_kernel(const UpBwdPrepParams p) {
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = __ldg(p.fir + (3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4));
+  __syncthreads();
+  const int Hp = p.H + 1, Wp = p.W + 1, Ho = 2 * p.H, Wo = 2 * p.W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Hp * Wp) return;
+  const int J = pix % Wp, I = pix / Wp;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const float* g0 = p.gz + (static_cast<size_t>(b) * (p.C / 4) + chunk * 2) * Ho * Wo * 4;
+  const float* g1 = g0 + static_cast<size_t>(Ho) * Wo * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[o][e] = 0.f;
+#pragma unroll
+  for (int dY = -2; dY <= 2; ++dY) {
+    const int Y = 2 * I + dY;
+    if (Y < 0 || Y >= Ho) continue;
+#pragma unroll
+    for (int dX = -2; dX <= 2; ++dX) {
+      const int X = 2 * J + dX;
+      if (X < 0 || X >= Wo) continue;
+      const size_t off = (static_cast<size_t>(Y) * Wo + X) * 4;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(g0 + off));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(g1 + off));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int pu = 0; pu < 2; ++pu) {
+        const int a = pu - dY + 1;
+        if (a < 0 || a > 3) continue;
+#pragma unroll
+        for (int pv = 0; pv < 2; ++pv) {
+          const int bq = pv - dX + 1;
+          if (bq < 0 || bq > 3) continue;
+          const float w = sk[a * 4 + bq];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[pu * 2 + pv][e] = fmaf(w, v[e], acc[pu * 2 + pv][e]);
+        }
+      }
+    }
+  }
+  const size_t plane_elems = static_cast<size_t>(p.B) * 4 * p.C * Hp * Wp;         // elements per hi/lo plane
+  const int chunks4 = 4 * (p.C / 8);
+#pragma unroll
+  for (int pl = 0; pl < 4; ++pl) {
+    const bool exists = (2 * I + (pl >> 1) <= 2 * p.H) && (2 * J + (pl & 1) <= 2 * p.W);   // inside the (2H+1)^2 grid
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      split2(exists ? acc[pl][2 * e] : 0.f, exists ? acc[pl][2 * e + 1] : 0.f, kFmtBF16, hp[e], lp[e]);
+    const size_t off = (((static_cast<size_t>(b) * chunks4 + pl * (p.C / 8) + chunk) * Hp + I) * Wp + J) * 8;
+    *reinterpret_cast<uint4*>(p.planes + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(p.planes + plane_elems + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
 }
 
@@ -222,6 +299,7 @@ struct BwdPlan {
   size_t grgb_off[SGR_MAX_RGB];
   size_t gz_off, gx_off[2];
   size_t splitk_off;
+  size_t planes_off;
   size_t total;
 };
 
@@ -271,6 +349,14 @@ static int plan_backward(const sgr_synthesis* net, int batch, BwdPlan* pl) {
     pl->gx_off[i] = off; off = align_up(off + max_in * 4, 256);
   }
   pl->splitk_off = off; off = align_up(off + kSplitKScratchBytes, 256);
+  size_t max_planes = 0;
+  for (int l = 0; l < net->n_styled; ++l)
+    if (net->styled[l].up == 2) {
+      const size_t res_in = static_cast<size_t>(4) << ((l + 1) / 2 - 1);
+      const size_t e = B * 4 * net->styled[l].cout * (res_in + 1) * (res_in + 1) * 4;
+      max_planes = max_planes > e ? max_planes : e;
+    }
+  pl->planes_off = off; off = align_up(off + max_planes, 256);
   pl->total = off;
   return 0;
 }
@@ -386,8 +472,10 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     p.noise = Ly.noise;
     p.noise_bstride = Ly.noise_batch_stride;
     p.noise_w = Ly.noise_weight;
-    p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
-    p.s2d = Ly.up ? 1 : 0;
+    const bool scatter = Ly.up == 2;      // gather adjoint: FIR^T to parity planes, then the 9 real taps
+    if (scatter) p.out_gz4 = F(pl.gz_off);
+    else p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
+    p.s2d = (Ly.up && !scatter) ? 1 : 0;
     p.act = 1;
     p.ds_next = gx_next ? F(pl.ds_off[l + 1]) : nullptr;
     p.q = F(pl.q_off[l]);
@@ -397,18 +485,33 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     sgr_conv_args a;
     memset(&a, 0, sizeof(a));
     a.batch = batch;
-    a.cin = Ly.up ? 4 * Ly.cout : Ly.cout;
+    if (scatter) {
+      if (!Ly.fir) {
+        set_error("synthesis_backward: layer %d (scatter up-conv) lacks its blur kernel", l);
+        return 1;
+      }
+      UpBwdPrepParams q;
+      q.B = batch; q.C = Ly.cout; q.H = res_in; q.W = res_in;
+      q.gz = F(pl.gz_off);
+      q.fir = Ly.fir;
+      q.planes = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_off);
+      dim3 grid(((res_in + 1) * (res_in + 1) + 127) / 128, Ly.cout / 8, batch);
+      up_bwd_prepare_kernel<<<grid, 128, 0, st>>>(q);
+      count_launch();
+      if (!check_launch("up_bwd_prepare_kernel")) return 1;
+    }
+    a.cin = scatter ? Ly.cout : (Ly.up ? 4 * Ly.cout : Ly.cout);
     a.cout = Ly.cin;
     a.h_in = res_in;
     a.w_in = res_in;
     a.ksize = 3;
-    a.up = 0;
+    a.up = scatter ? 3 : 0;
     a.act = 0;
     a.act_gain = 1.f;
     a.operand_format = SGR_FMT_BF16;      // gradients have no a-priori range: bf16 split (fp32 exponent)
     a.out_format = SGR_FMT_BF16;
     a.column_tile = Ly.column_tile_t;
-    a.x_c8 = ws + pl.gz_off;
+    a.x_c8 = scatter ? ws + pl.planes_off : ws + pl.gz_off;
     a.w_packed = Ly.w_packed_t;
     a.out_f32 = F(pl.gx_off[gx_cur]);
     a.splitk_scratch = ws + pl.splitk_off;

@@ -111,14 +111,13 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         const int k0 = ks * k_iters / p.ksplit, k1 = (ks + 1) * k_iters / p.ksplit;
         int tap = k0 / p.kchunks, kc = k0 - tap * p.kchunks;
         for (int k = k0; k < k1; ++k, ++it) {
-          const int dy = (p.ntaps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.ntaps == 9) ? tap % 3 - 1 : 0;
+          const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
           const uint32_t s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = stage_base + s * Cfg::kStageBytes;
           mbar_expect_tx(&full[s], a_bytes + Cfg::kBBytes);
-          tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, kc * 4, 0);
+          tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, p.tap_chunk[tap] + kc * 4, 0);
           bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(k) * (NT * 64), Cfg::kBBytes, &full[s]);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
         }
@@ -402,8 +401,8 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
     set_error("modconv: up requires ksize 3");
     return 1;
   }
-  if (a->up < 0 || a->up > 2 || (a->up == 2 && (!a->t_scratch || !a->fir || !a->demod))) {
-    set_error("modconv: up must be 0, 1 (polyphase) or 2 (scatter + FIR; needs t_scratch, fir and demod)");
+  if (a->up < 0 || a->up > 3 || (a->up == 2 && (!a->t_scratch || !a->fir || !a->demod))) {
+    set_error("modconv: up must be 0, 1 (polyphase), 2 (scatter + FIR; needs t_scratch, fir and demod) or 3 (gather adjoint)");
     return 1;
   }
   if (a->noise && !a->noise_weight) {
@@ -415,7 +414,7 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
     return 1;
   }
   p->B = a->batch;
-  p->mode = a->up;
+  p->mode = a->up == 3 ? 0 : a->up;
   { const char* e = getenv("SGR_DEBUG"); p->debug = e ? atoi(e) : 0; }
   if (a->up == 2) {               // tiles walk the (H+1) x (W+1) parity-plane grid
     p->H = a->h_in + 1;
@@ -438,7 +437,7 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->tiles_y = (p->H + p->bh - 1) / p->bh;
   p->tiles_b = (a->batch + p->bb - 1) / p->bb;
   p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
-  const int n_total = a->cout * (a->up ? 4 : 1);
+  const int n_total = a->cout * ((a->up == 1 || a->up == 2) ? 4 : 1);
   if (a->up == 2) {
     *nt = up2_nt(a->cout);        // [oe|ee|eo|oo] blocks of NT/4 channels; fixed by the packed layout
     if (a->column_tile > 0 && a->column_tile != *nt) {
@@ -455,11 +454,28 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   p->n_tiles = n_total / *nt;
   p->kchunks = a->cin / kBlockK;
   p->ntaps = a->up == 2 ? 4 : a->ksize * a->ksize;
+  for (int t = 0; t < 9; ++t) {
+    p->tap_dy[t] = static_cast<signed char>(p->ntaps == 9 ? t / 3 - 1 : 0);
+    p->tap_dx[t] = static_cast<signed char>(p->ntaps == 9 ? t % 3 - 1 : 0);
+    p->tap_chunk[t] = 0;
+  }
+  if (a->up == 3) {
+    // gather adjoint of the scatter up-conv: x_c8 holds the four parity planes [ee|eo|oe|oo] of the FIR^T-filtered
+    // gradient stacked as 4*cin channels on the (h_in+1) x (w_in+1) grid; tap t = (plane, shift (a,b))
+    static const int plane[9] = {0, 0, 0, 0, 1, 1, 2, 2, 3};
+    static const int sa[9] = {0, 0, 1, 1, 0, 1, 0, 0, 0};
+    static const int sb[9] = {0, 1, 0, 1, 0, 0, 0, 1, 0};
+    for (int t = 0; t < 9; ++t) {
+      p->tap_dy[t] = static_cast<signed char>(sa[t]);
+      p->tap_dx[t] = static_cast<signed char>(sb[t]);
+      p->tap_chunk[t] = plane[t] * (a->cin / 8);
+    }
+  }
   p->cout = a->cout;
   p->up = a->up == 1 ? 1 : 0;
   p->t_out = a->t_scratch;
-  p->Hout = a->up ? 2 * a->h_in : a->h_in;
-  p->Wout = a->up ? 2 * a->w_in : a->w_in;
+  p->Hout = (a->up == 1 || a->up == 2) ? 2 * a->h_in : a->h_in;
+  p->Wout = (a->up == 1 || a->up == 2) ? 2 * a->w_in : a->w_in;
   p->act = a->act;
   p->act_gain = a->act_gain;
   if ((a->operand_format != SGR_FMT_BF16 && a->operand_format != SGR_FMT_FP16) ||

@@ -34,6 +34,13 @@ __device__ float effective_weight(const float* __restrict__ w, const float* __re
     return acc;
   }
   // adjoint: column n = input channel i; reduction index = (phase,) output channel o; tap offsets negate.
+  if (up == 2) {
+    // gather adjoint of the scatter up-conv: tap t reads parity plane (ee x4, eo x2, oe x2, oo) of the FIR^T-filtered
+    // gradient at shift (a,b) and multiplies W[o][i][ky][kx] with (ky,kx) = (pu + 2a, pv + 2b) (kScatterAdjTaps)
+    const int ky = tap < 4 ? 2 * (tap >> 1) : (tap < 6 ? 2 * (tap - 4) : 1);
+    const int kx = tap < 4 ? 2 * (tap & 1) : (tap < 6 ? 1 : (tap < 8 ? 2 * (tap - 6) : 1));
+    return scale * w[((static_cast<size_t>(kidx) * cin + n) * 3 + ky) * 3 + kx];
+  }
   if (!up) {
     const int o = kidx;
     return scale * w[((static_cast<size_t>(o) * cin + n) * ks + (ks / 2 - dy)) * ks + (ks / 2 - dx)];
@@ -368,9 +375,9 @@ int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int 
     }
     return 0;
   }
-  if (up) up = 1;
+  if (up && !(up == 2 && transpose)) up = 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
-  const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
+  const int k_total = transpose ? cout * (up == 1 ? 4 : 1) : cin;
   const int nt = nt_req > 0 ? nt_req : pick_nt(n_total);
   const long long rows = static_cast<long long>(n_total) * ks * ks * (k_total / 8);
   const int threads = 256;

@@ -171,7 +171,7 @@ int sgr_choose_column_tile(int batch, int h_in, int w_in, int n_total) {
 }
 
 size_t sgr_packed_weight_bytes(int cout, int cin, int ksize, int up, int transpose) {
-  if (up == 2 && !transpose) return static_cast<size_t>(cout) * cin * 9 * 2 * 2;   // scatter: the 9 real taps
+  if (up == 2) return static_cast<size_t>(cout) * cin * 9 * 2 * 2;   // scatter / its gather adjoint: the 9 real taps
   const size_t n_total = transpose ? cin : static_cast<size_t>(cout) * (up ? 4 : 1);
   const size_t k_total = transpose ? static_cast<size_t>(cout) * (up ? 4 : 1) : cin;
   return n_total * k_total * ksize * ksize * 2 /*planes*/ * 2 /*bf16*/;
@@ -185,7 +185,7 @@ int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int
                             int format, int column_tile, void* packed, float* wsq, void* stream) {
   if (!have_device()) return 1;
   const int n_total = transpose ? cin : cout * (up ? 4 : 1);
-  const int k_total = transpose ? cout * (up ? 4 : 1) : cin;
+  const int k_total = transpose ? cout * (up == 1 ? 4 : 1) : cin;
   if (up == 2 && !transpose) {
     if (!weight || !packed || ksize != 3 || cin % kBlockK != 0 || cout < 32 || (cout & (cout - 1)) != 0 ||
         (format != SGR_FMT_BF16 && format != SGR_FMT_FP16) || (column_tile != 0 && column_tile != up2_nt(cout))) {
@@ -196,7 +196,7 @@ int sgr_pack_modconv_weight(const float* weight, const float* fir, int cout, int
     return pack_weight_launch(weight, fir, cout, cin, ksize, 2, 0, format, column_tile, packed, wsq,
                               static_cast<cudaStream_t>(stream));
   }
-  if (!weight || !packed || (up && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
+  if (!weight || !packed || (up == 1 && !fir) || (ksize != 3 && ksize != 1) || (up && ksize != 3) ||
       k_total % kBlockK != 0 || n_total < 32 || (n_total & (n_total - 1)) != 0 ||
       (format != SGR_FMT_BF16 && format != SGR_FMT_FP16) ||
       (column_tile != 0 && (column_tile > n_total || n_total % column_tile != 0 ||
@@ -232,7 +232,12 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
     return rc;
   }
   CUtensorMap tmap;
-  if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) return 1;
+  if (args->up == 3) {       // gather adjoint: the operand is the 4-plane tensor on the (h+1) x (w+1) grid
+    if (make_act_tensor_map(&tmap, args->x_c8, args->batch, 4 * args->cin, args->h_in + 1, args->w_in + 1, p.bw, p.bh, p.bb))
+      return 1;
+  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) {
+    return 1;
+  }
   if (args->up != 2)
     set_ksplit(&p, choose_ksplit(args, p.m_tiles * p.n_tiles, p.ntaps * p.kchunks, 8, static_cast<size_t>(kTileM) * nt * 4));
   const bool prof = prof_begin(static_cast<cudaStream_t>(stream));

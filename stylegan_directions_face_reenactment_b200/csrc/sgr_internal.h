@@ -43,6 +43,8 @@ struct ConvKernelParams {
   int m_tiles, n_tiles;
   int kchunks;                  // cin / 32
   int ntaps;                    // 9 or 1
+  signed char tap_dy[9], tap_dx[9];   // pixel shift of tap t
+  int tap_chunk[9];             // first 8-channel chunk of tap t's operand (parity planes stacked as channels)
   int cout;                     // real output channels (power of two)
   int up;
   int Hout, Wout;

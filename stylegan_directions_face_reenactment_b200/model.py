@@ -182,8 +182,10 @@ class ModulatedConv2d(nn.Module):
             self._pack_cache.clear()
             self._pack_cache['version'] = version
         # upsampling layers: forward operator in scatter form (up=2: 9 real taps + FIR pass), adjoint in polyphase form
-        up_mode = 0 if not self.upsample else (1 if transpose else self.up_mode())
-        if up_mode == 2:
+        # (up=2: forward = 9-tap scatter conv + FIR pass, adjoint = FIR^T to parity planes + 9-tap gather conv; up=1: both
+        # in polyphase form, for a blur kernel that is not an outer product)
+        up_mode = self.up_mode()
+        if up_mode == 2 and not transpose:
             nt = 0                                               # fixed by the scatter layout
         slot = (bool(transpose), fmt, nt, up_mode)
         hit = self._pack_cache.get(slot)
