@@ -35,6 +35,7 @@ struct BwdActParams {
   float* out_gz4;         // gz as fp32 [B][C/4][H][W][4] (scatter-form up layers: input of up_bwd_prepare_kernel) or NULL
   int s2d;
   int act;                // 0: constant-input pseudo layer (only the ds reduction)
+  int iters;              // pixel iterations per thread (set by bwd_act_launch)
   float* ds_next;         // [B,C] += sum_p a * gx
   float* q;               // [B,C] += sum_p gt * (t - noise - bias)
   float* ds_rgb;          // [B,C] += sum_p a * sum_c grgb*wrgb/sqrt(C)
@@ -46,117 +47,143 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// grid: (pixel groups, C/8, B); each thread: 4 consecutive pixels x 8 channels.
-__global__ void __launch_bounds__(128) bwd_act_kernel(const BwdActParams p) {
+// grid: (pixel spans, C/8, B); a thread handles 1 pixel x 8 channels per iteration and `iters` iterations
+// (block stride), keeps the three per-(b,c) sums in registers, and the block issues ONE atomic per sum and channel at
+// the end (one warp-reduction + atomic per iteration put 1.6 M atomics on 1024 addresses at 256^2: 4x off the HBM time).
+constexpr int kBwdActThreads = 256;
+__global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdActParams p) {
+  __shared__ float red[kBwdActThreads / 32][24];
   const int HW = p.H * p.W;
-  const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const bool valid = pix < HW;
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 8;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float kSqrt2 = 1.4142135623730951f, kInvSqrt2 = 0.7071067811865476f;
-  float g3[3][4];
-  float nz[4] = {0.f, 0.f, 0.f, 0.f};
-  if (valid) {
+  const float rs = rsqrtf(static_cast<float>(p.C));
+  const float nw = p.noise ? __ldg(p.noise_w) : 0.f;
+  // per-channel constants live in shared memory (56 registers otherwise: 25 % occupancy on an HBM-latency-bound kernel)
+  __shared__ float sn[8], w0[8], w1[8], w2[8], sr[8], dm[8], bi[8];
+  if (threadIdx.x < 8) {
+    const int e = threadIdx.x, c = c0 + e;
+    sn[e] = p.gx ? __ldg(p.s_next + static_cast<size_t>(b) * p.C + c) : 0.f;
+    w0[e] = w1[e] = w2[e] = sr[e] = 0.f;
+    if (p.grgb) {
+      w0[e] = __ldg(p.wrgb + c) * rs;
+      w1[e] = __ldg(p.wrgb + p.C + c) * rs;
+      w2[e] = __ldg(p.wrgb + 2 * p.C + c) * rs;
+      sr[e] = __ldg(p.s_rgb + static_cast<size_t>(b) * p.C + c);
+    }
+    dm[e] = p.act ? __ldg(p.demod + static_cast<size_t>(b) * p.C + c) : 1.f;
+    bi[e] = (p.act && p.bias) ? __ldg(p.bias + c) : 0.f;
+  }
+  __syncthreads();
+  float dsn[8], qa[8], dsr[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dsn[e] = qa[e] = dsr[e] = 0.f;
+
+  // one pixel per thread and iteration: consecutive lanes read consecutive floats of every channel plane (128 B per warp
+  // and channel) and write consecutive 16 B operand chunks (4 pixels per thread made every store instruction touch
+  // 32 sectors for 512 B: 28 % excess sectors)
+  for (int it = 0; it < p.iters; ++it) {
+    const int pix = (blockIdx.x * p.iters + it) * kBwdActThreads + threadIdx.x;
+    if (pix >= HW) break;
+    float g3[3] = {0.f, 0.f, 0.f};
     if (p.grgb) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.grgb + (static_cast<size_t>(b) * 3 + c) * HW + pix));
-        g3[c][0] = g.x; g3[c][1] = g.y; g3[c][2] = g.z; g3[c][3] = g.w;
-      }
+      for (int c = 0; c < 3; ++c) g3[c] = __ldg(p.grgb + (static_cast<size_t>(b) * 3 + c) * HW + pix);
     }
-    if (p.noise) {
-      const float nw = __ldg(p.noise_w);
-      const float4 n = __ldg(reinterpret_cast<const float4*>(p.noise + static_cast<size_t>(b) * p.noise_bstride + pix));
-      nz[0] = nw * n.x; nz[1] = nw * n.y; nz[2] = nw * n.z; nz[3] = nw * n.w;
-    }
-  }
-  const float rs = rsqrtf(static_cast<float>(p.C));
-  float gzv[4][8];
+    const float nz = p.noise ? nw * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride + pix) : 0.f;
+    float av[8], gxv[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    float dsn = 0.f, qa = 0.f, dsr = 0.f;
-    if (valid) {
-      const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(b) * p.a_bstride +
-                                                               static_cast<size_t>(c) * HW + pix));
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      float gxv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.gx) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gx + (static_cast<size_t>(b) * p.C + c) * HW + pix));
-        gxv[0] = g.x; gxv[1] = g.y; gxv[2] = g.z; gxv[3] = g.w;
-      }
-      const float sn = p.gx ? __ldg(p.s_next + static_cast<size_t>(b) * p.C + c) : 0.f;
-      float w0 = 0.f, w1 = 0.f, w2 = 0.f, sr = 0.f;
+    for (int e = 0; e < 8; ++e) {
+      av[e] = __ldg(p.a + static_cast<size_t>(b) * p.a_bstride + static_cast<size_t>(c0 + e) * HW + pix);
+      gxv[e] = p.gx ? __ldg(p.gx + (static_cast<size_t>(b) * p.C + c0 + e) * HW + pix) : 0.f;
+    }
+    float gzv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = av[e];
+      float ga = gxv[e] * sn[e];
+      dsn[e] = fmaf(a, gxv[e], dsn[e]);
       if (p.grgb) {
-        w0 = __ldg(p.wrgb + c) * rs;
-        w1 = __ldg(p.wrgb + p.C + c) * rs;
-        w2 = __ldg(p.wrgb + 2 * p.C + c) * rs;
-        sr = __ldg(p.s_rgb + static_cast<size_t>(b) * p.C + c);
+        const float r = fmaf(g3[0], w0[e], fmaf(g3[1], w1[e], g3[2] * w2[e]));
+        ga = fmaf(r, sr[e], ga);
+        dsr[e] = fmaf(a, r, dsr[e]);
       }
-      const float d = p.act ? __ldg(p.demod + static_cast<size_t>(b) * p.C + c) : 1.f;
-      const float bi = (p.act && p.bias) ? __ldg(p.bias + c) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = av[j];
-        float ga = gxv[j] * sn;
-        dsn = fmaf(a, gxv[j], dsn);
-        if (p.grgb) {
-          const float r = fmaf(g3[0][j], w0, fmaf(g3[1][j], w1, g3[2][j] * w2));
-          ga = fmaf(r, sr, ga);
-          dsr = fmaf(a, r, dsr);
-        }
-        if (p.act) {
-          const bool pos = a > 0.f;
-          const float gt = ga * (pos ? kSqrt2 : 0.2f * kSqrt2);
-          const float t = pos ? a * kInvSqrt2 : a * (5.f * kInvSqrt2);
-          qa = fmaf(gt, t - nz[j] - bi, qa);
-          gzv[j][e] = gt * d;
-        }
+      gzv[e] = 0.f;
+      if (p.act) {
+        const bool pos = a > 0.f;
+        const float gt = ga * (pos ? kSqrt2 : 0.2f * kSqrt2);
+        const float t = pos ? a * kInvSqrt2 : a * (5.f * kInvSqrt2);
+        qa[e] = fmaf(gt, t - nz - bi[e], qa[e]);
+        gzv[e] = gt * dm[e];
       }
     }
-    dsn = warp_sum(dsn);
-    if (p.act) qa = warp_sum(qa);
-    if (p.grgb) dsr = warp_sum(dsr);
-    if (lane == 0) {
-      const size_t o = static_cast<size_t>(b) * p.C + c;
-      if (p.ds_next && p.gx) atomicAdd(p.ds_next + o, dsn);
-      if (p.act) atomicAdd(p.q + o, qa);
-      if (p.grgb) atomicAdd(p.ds_rgb + o, dsr);
+    if (p.out_gz4 && p.act) {
+      float* dst = p.out_gz4 + ((static_cast<size_t>(b) * (p.C / 4) + blockIdx.y * 2) * HW + pix) * 4;
+      *reinterpret_cast<float4*>(dst) = make_float4(gzv[0], gzv[1], gzv[2], gzv[3]);
+      *reinterpret_cast<float4*>(dst + static_cast<size_t>(HW) * 4) = make_float4(gzv[4], gzv[5], gzv[6], gzv[7]);
     }
-  }
-  if (valid && p.out_gz4 && p.act) {
-    const int y = pix / p.W, x = pix % p.W;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      float4* dst = reinterpret_cast<float4*>(p.out_gz4 + (((static_cast<size_t>(b) * (p.C / 4) + blockIdx.y * 2 + g) * p.H + y) * p.W + x) * 4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = make_float4(gzv[j][4 * g], gzv[j][4 * g + 1], gzv[j][4 * g + 2], gzv[j][4 * g + 3]);
-    }
-  }
-  if (valid && p.out_c8 && p.act) {
-    const int y = pix / p.W, x = pix % p.W;
-    const int chunks = p.C / 8;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      size_t off, plane;
+    if (p.out_c8 && p.act) {
+      const int chunks = p.C / 8;
+      size_t off;
       if (!p.s2d) {
-        off = ((static_cast<size_t>(b) * chunks + blockIdx.y) * p.H + y) * p.W + x + j;
-        plane = static_cast<size_t>(p.B) * chunks * HW;
+        off = (static_cast<size_t>(b) * chunks + blockIdx.y) * HW + pix;
       } else {
-        const int phase = (y & 1) * 2 + ((x + j) & 1);
+        const int y = pix / p.W, x = pix - y * p.W;
+        const int phase = (y & 1) * 2 + (x & 1);
         const int H2 = p.H / 2, W2 = p.W / 2;
-        off = ((static_cast<size_t>(b) * (4 * chunks) + phase * chunks + blockIdx.y) * H2 + (y >> 1)) * W2 + ((x + j) >> 1);
-        plane = static_cast<size_t>(p.B) * chunks * HW;      // 4*chunks * H2*W2 == chunks * HW
+        off = ((static_cast<size_t>(b) * (4 * chunks) + phase * chunks + blockIdx.y) * H2 + (y >> 1)) * W2 + (x >> 1);
       }
+      const size_t plane = static_cast<size_t>(p.B) * chunks * HW;        // 16-byte rows per hi/lo plane
       uint32_t hp[4], lp[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split2(gzv[j][2 * e], gzv[j][2 * e + 1], kFmtBF16, hp[e], lp[e]);
+      for (int e = 0; e < 4; ++e) split2(gzv[2 * e], gzv[2 * e + 1], kFmtBF16, hp[e], lp[e]);
       uint4* o4 = reinterpret_cast<uint4*>(p.out_c8);
       o4[off] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       o4[plane + off] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
   }
+
+  // block reduction of the 24 sums, then one atomic each
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    dsn[e] = warp_sum(dsn[e]);
+    qa[e] = warp_sum(qa[e]);
+    dsr[e] = warp_sum(dsr[e]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][e] = dsn[e];
+      red[warp][8 + e] = qa[e];
+      red[warp][16 + e] = dsr[e];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 24) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdActThreads / 32; ++w) v += red[w][threadIdx.x];
+    const int kind = threadIdx.x >> 3, e = threadIdx.x & 7;
+    const size_t o = static_cast<size_t>(b) * p.C + c0 + e;
+    if (kind == 0 && p.ds_next && p.gx) atomicAdd(p.ds_next + o, v);
+    if (kind == 1 && p.act) atomicAdd(p.q + o, v);
+    if (kind == 2 && p.grgb) atomicAdd(p.ds_rgb + o, v);
+  }
+}
+
+static int bwd_act_launch(BwdActParams p, cudaStream_t st) {
+  const int HW = p.H * p.W;
+  const int groups = (HW + kBwdActThreads - 1) / kBwdActThreads;           // thread-iterations along the pixels
+  // enough blocks to fill the machine, as few atomics as possible
+  const long long others = static_cast<long long>(p.C / 8) * p.B;
+  int iters = 1;
+  while (iters < 16 && (groups / (iters * 2)) * others >= 2048) iters *= 2;
+  p.iters = iters;
+  dim3 grid((groups + iters - 1) / iters, p.C / 8, p.B);
+  bwd_act_kernel<<<grid, kBwdActThreads, 0, st>>>(p);
+  count_launch();
+  return check_launch("bwd_act_kernel") ? 0 : 1;
 }
 
 // Scatter-form up layers, backward: G = FIR^T(gz) on the (2H+1)^2 grid of conv_transpose2d outputs, split into its four
@@ -226,14 +253,6 @@ __global__ void __launch_bounds__(128) up_bwd_prepare_kernel(const UpBwdPrepPara
     *reinterpret_cast<uint4*>(p.planes + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
     *reinterpret_cast<uint4*>(p.planes + plane_elems + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
-}
-
-static int bwd_act_launch(const BwdActParams& p, cudaStream_t st) {
-  const int HW = p.H * p.W;
-  dim3 grid((HW / 4 + 127) / 128, p.C / 8, p.B);
-  bwd_act_kernel<<<grid, 128, 0, st>>>(p);
-  count_launch();
-  return check_launch("bwd_act_kernel") ? 0 : 1;
 }
 
 // ds[b,i] = ds_conv[b,i] - s[b,i] * sum_o q[b,o] d[b,o]^2 wsq[o,i]      (in place on ds_conv)
