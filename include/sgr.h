@@ -68,6 +68,12 @@ int sgr_upfirdn2d(const float* x, float* y, const float* taps, int planes, int i
 int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, float* y, long long outer, int channels,
                        long long inner, int grad, float slope, float scale, void* stream);
 
+/* Output stage: frames [B,3,h,w] fp32 in [-1,1] -> uint8 [B,out_h,out_w,3] (HWC, RGB order) with the
+ * reference's arithmetic  uint8((clamp(x,-1,1) + 1) / (2 + 1e-5) * 255)  (libs/utilities/image_utils.py:97-111, np.uint8 at
+ * libs/utilities/utils_inference.py:16); out_h/out_w < h/w additionally applies the block-mean AdaptiveAvgPool2d of
+ * generate_image (libs/utilities/generic.py:146-148; h % out_h == 0, w % out_w == 0).  4x less device->host traffic. */
+int sgr_frames_to_uint8(const float* frames, unsigned char* out, int batch, int h, int w, int out_h, int out_w, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Weight packing for the tcgen05 implicit-GEMM convolution.
  * weight: [cout, cin, k, k] fp32 (the reference parameter ModulatedConv2d.weight[0], model.py:216-218), k = 3 or 1.

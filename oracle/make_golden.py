@@ -210,11 +210,31 @@ def golden_reenact():
          gA_b=A.linear.bias.grad)
 
 
+def golden_output_stage():
+    """tensor_to_image (libs/utilities/image_utils.py:97-111) + np.uint8 (utils_inference.py:16) on seeded frames, and the
+    256-pooling of generate_image (generic.py:146-148) in front of it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_image_utils', os.path.join('/root/reference', 'libs', 'utilities', 'image_utils.py'))
+    iu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(iu)
+    rng = np.random.Generator(np.random.PCG64(41))
+    x = rnd(rng, 2, 3, 32, 32) * 0.8
+    x[0, :, 0, :4] = torch.tensor([-1.0, 1.0, -3.0, 5.0])
+    y = np.stack([np.uint8(iu.tensor_to_image(x[i:i + 1].clone())) for i in range(2)])
+    pooled = torch.nn.AdaptiveAvgPool2d((8, 8))(x)
+    yp = np.stack([np.uint8(iu.tensor_to_image(pooled[i:i + 1].clone())) for i in range(2)])
+    save('output_stage.npz', x=x, y=y, y_pooled=yp)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'output_stage':
+        golden_output_stage()
+        sys.exit(0)
     golden_upfirdn2d()
     golden_bias_act()
     golden_modconv()
     golden_styled_block()
     golden_generator()
     golden_reenact()
+    golden_output_stage()

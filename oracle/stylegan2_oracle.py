@@ -342,3 +342,16 @@ def forward_flops_per_frame(size, channel_multiplier):
         fl += 2 * cin * cout * 9 * hin * hin + 2 * cout * cout * 9 * hout * hout + 2 * cout * 3 * hout * hout
         cin = cout
     return fl
+
+
+def frames_to_uint8(images, size=None):
+    """Output stage as the reference does it: optional AdaptiveAvgPool2d (generic.py:146-148), tensor_to_image
+    (libs/utilities/image_utils.py:97-111) and np.uint8 (libs/utilities/utils_inference.py:16).  [B,3,H,W] -> uint8 [B,h,w,3]."""
+    import numpy as np
+    x = images.detach().float().clone()
+    if size is not None and x.shape[2] > size:
+        x = F.adaptive_avg_pool2d(x, (size, size))
+    x.clamp_(min=-1, max=1)
+    x.add_(1).div_(1 - (-1) + 1e-5)
+    x = x.mul(255.0).add(0.0)
+    return np.uint8(np.transpose(x.numpy(), (0, 2, 3, 1)))

@@ -67,6 +67,7 @@ SIGNATURES = {
     'sgr_upfirdn2d': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 9 + [_fp]),
     'sgr_fused_bias_act': (C.c_int, [_fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                      C.c_float, _fp]),
+    'sgr_frames_to_uint8': (C.c_int, [_fp, _fp] + [C.c_int] * 5 + [_fp]),
     'sgr_packed_weight_bytes': (C.c_size_t, [C.c_int] * 5),
     'sgr_up_scratch_bytes': (C.c_size_t, [C.c_int] * 4),
     'sgr_pack_modconv_weight': (C.c_int, [_fp, _fp] + [C.c_int] * 7 + [_fp, _fp, _fp]),

@@ -165,6 +165,15 @@ int sgr_fused_bias_act(const float* x, const float* bias, const float* ref, floa
   return bias_act_launch(x, bias, ref, y, outer, channels, inner, grad, slope, scale, static_cast<cudaStream_t>(stream));
 }
 
+int sgr_frames_to_uint8(const float* frames, unsigned char* out, int batch, int h, int w, int out_h, int out_w, void* stream) {
+  if (!have_device()) return 1;
+  if (!frames || !out) {
+    set_error("frames_to_uint8: null pointer");
+    return 1;
+  }
+  return frames_to_uint8_launch(frames, out, batch, h, w, out_h, out_w, static_cast<cudaStream_t>(stream));
+}
+
 int sgr_choose_column_tile(int batch, int h_in, int w_in, int n_total) {
   if (batch <= 0 || h_in <= 0 || w_in <= 0 || n_total < 32) return 0;
   return choose_nt(batch, h_in, w_in, n_total);

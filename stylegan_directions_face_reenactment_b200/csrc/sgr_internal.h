@@ -136,6 +136,7 @@ int bias_act_launch(const float* x, const float* bias, const float* ref, float* 
                     long long inner, int grad, float slope, float scale, cudaStream_t st);
 int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
                       float* out, int batch, int H, int W, cudaStream_t st);
+int frames_to_uint8_launch(const float* x, unsigned char* y, int batch, int H, int W, int out_h, int out_w, cudaStream_t st);
 // up_finish_sm100.cu: FIR + fused epilogue over the parity planes of a scatter up-conv
 int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st);
 bool acc_comp_enabled();

@@ -272,4 +272,52 @@ int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const 
   return check_launch("torgb_tail_kernel") ? 0 : 1;
 }
 
+// ------------------------------------------------------------------------------------------------ output stage
+// Frames [B,3,H,W] fp32 in [-1,1] -> uint8 [B,H,W,3] exactly as the reference post-processing does on the way to the
+// video writer (libs/utilities/image_utils.py:97-111 tensor_to_image + np.uint8 at utils_inference.py:16):
+//   v = clamp(x, -1, 1);  v = (v + 1) / (2 + 1e-5) * 255;  uint8(v)  (truncation toward zero)
+// optionally after the AdaptiveAvgPool2d(256) of generate_image for larger nets (generic.py:146-148; H, W multiples of
+// out_h, out_w: each output pixel is the mean of an (H/out_h) x (W/out_w) block).  One thread per output pixel, the three
+// channels of a pixel are written as 3 adjacent bytes (coalesced over x).
+__global__ void frames_to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ y, int batch, int H, int W,
+                                       int out_h, int out_w) {
+  const long long total = static_cast<long long>(batch) * out_h * out_w;
+  const int fy = H / out_h, fx = W / out_w;
+  const float inv_area = 1.f / static_cast<float>(fy * fx);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(idx % out_w);
+    const int oy = static_cast<int>((idx / out_w) % out_h);
+    const int b = static_cast<int>(idx / (static_cast<long long>(out_w) * out_h));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* src = x + ((static_cast<size_t>(b) * 3 + c) * H + static_cast<size_t>(oy) * fy) * W + static_cast<size_t>(ox) * fx;
+      float v = 0.f;
+      if (fy == 1 && fx == 1) {
+        v = __ldg(src);
+      } else {
+        for (int dy = 0; dy < fy; ++dy)
+          for (int dx = 0; dx < fx; ++dx) v += __ldg(src + static_cast<size_t>(dy) * W + dx);
+        v *= inv_area;
+      }
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      v = __fdiv_rn(v + 1.f, 2.00001f) * 255.f;
+      y[idx * 3 + c] = static_cast<unsigned char>(static_cast<int>(v));
+    }
+  }
+}
+
+int frames_to_uint8_launch(const float* x, unsigned char* y, int batch, int H, int W, int out_h, int out_w, cudaStream_t st) {
+  if (batch <= 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || H % out_h != 0 || W % out_w != 0) {
+    set_error("frames_to_uint8: output %dx%d must divide the frame size %dx%d", out_h, out_w, H, W);
+    return 1;
+  }
+  const long long total = static_cast<long long>(batch) * out_h * out_w;
+  const long long blocks = (total + 255) / 256;
+  frames_to_uint8_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(x, y, batch, H, W, out_h,
+                                                                                                  out_w);
+  count_launch();
+  return check_launch("frames_to_uint8_kernel") ? 0 : 1;
+}
+
 }  // namespace sgr

@@ -35,3 +35,26 @@ def generate_image(G, latent_code, truncation, trunc, w_plus=True, num_layers_sh
     if imgs.shape[2] > 256:
         imgs = torch.nn.functional.adaptive_avg_pool2d(imgs, (256, 256))
     return (imgs, latents) if return_latents else imgs
+
+
+def frames_to_uint8(images, size=None):
+    """Fused output stage: [B,3,H,W] fp32 frames in [-1,1] -> [B,h,w,3] uint8 CUDA tensor with the
+    arithmetic of the reference's tensor_to_image + np.uint8 (libs/utilities/image_utils.py:97-111,
+    libs/utilities/utils_inference.py:16); `size` < H also applies generate_image's 256-pooling (generic.py:146-148).
+    One kernel, a quarter of the device->host bytes of the fp32 frames."""
+    from . import _native as N
+    if not images.is_cuda:
+        raise RuntimeError('frames_to_uint8: CUDA tensor required (no CPU fallback)')
+    x = images.detach().contiguous().float()
+    if x.ndim == 3:
+        x = x.unsqueeze(0)
+    b, c, h, w = x.shape
+    if c != 3:
+        raise RuntimeError('frames_to_uint8 expects RGB frames [B,3,H,W], got %s' % (tuple(images.shape),))
+    oh = ow = size if size is not None else None
+    if oh is None:
+        oh, ow = h, w
+    out = torch.empty(b, oh, ow, 3, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().sgr_frames_to_uint8(N.ptr(x), N.ptr(out), b, h, w, oh, ow, N.stream()), 'sgr_frames_to_uint8')
+    return out

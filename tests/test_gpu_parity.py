@@ -411,3 +411,21 @@ def test_single_pass_bf16_mode_reports_parity(pkg, monkeypatch):
     rng_ = ref.abs().max().item()
     print('bf16 single-pass: max-abs %.3e on range %.2f' % (e, rng_))
     assert 1e-5 < e <= 2e-2 * rng_
+
+
+def test_frames_to_uint8_output_stage(pkg):
+    """fused clamp / scale / uint8 / HWC (+ 256-pooling) against the reference arithmetic.  Integer output:
+    bit-exact except where the fp32 value sits within one rounding of an integer boundary (division vs the oracle's)."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    x = T((rng.standard_normal((3, 3, 64, 64), dtype=np.float32) * 0.8))
+    x[0, 0, 0, :4] = T(np.array([-1.0, 1.0, -3.0, 5.0], dtype=np.float32))
+    y = pkg.frames_to_uint8(x.cuda()).cpu().numpy()
+    ref = orc.frames_to_uint8(x)
+    assert y.shape == ref.shape == (3, 64, 64, 3) and y.dtype == np.uint8
+    diff = np.abs(y.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert y[0, 0, 0, 0] == 0 and y[0, 0, 1, 0] == 254 and y[0, 0, 2, 0] == 0 and y[0, 0, 3, 0] == 254   # (2/2.00001*255 -> 254)
+    yp = pkg.frames_to_uint8(x.cuda(), size=16).cpu().numpy()
+    refp = orc.frames_to_uint8(x, size=16)
+    dp = np.abs(yp.astype(np.int32) - refp.astype(np.int32))
+    assert yp.shape == (3, 16, 16, 3) and dp.max() <= 1 and (dp != 0).mean() < 2e-2

@@ -132,3 +132,11 @@ def test_scatter_upconv_algebra_matches_reference_form():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main() < 1e-12
+
+
+def test_output_stage_golden(golden):
+    """oracle.frames_to_uint8 == the reference's tensor_to_image + np.uint8 (+ AdaptiveAvgPool2d), bit-exact on CPU."""
+    g = golden('output_stage.npz')
+    x = torch.from_numpy(g['x'])
+    assert np.array_equal(orc.frames_to_uint8(x), g['y'])
+    assert np.array_equal(orc.frames_to_uint8(x, size=8), g['y_pooled'])
