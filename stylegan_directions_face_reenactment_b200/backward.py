@@ -4,7 +4,7 @@ import ctypes as C
 import torch
 
 from . import _native as N
-from .synthesis import NetDescriptor, _workspace
+from .synthesis import _descriptor, _workspace
 
 
 def synthesis_backward(g, lat, feats, noise, grad_image):
@@ -14,7 +14,7 @@ def synthesis_backward(g, lat, feats, noise, grad_image):
     dev = lat.device
     gimg = grad_image.contiguous().float()
     with torch.cuda.device(dev):
-        desc = NetDescriptor(g, noise, batch, backward=True)
+        desc = _descriptor(g, noise, batch, backward=True)
         ws = _workspace(g, desc, batch, dev, backward=True)
         dlat = torch.empty_like(lat)
         arr = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])

@@ -44,17 +44,24 @@ __global__ void __launch_bounds__(128) splitk_finish_kernel(const ConvKernelPara
   for (int c = 0; c < nt; c += 32) {
     float v[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(src + c + 4 * q);
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-    for (int ks = 1; ks < p.ksplit; ++ks) {
-      const float* sp = src + ks * slice_stride + c;
+    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+    // slices are added in order (deterministic); four slices' loads are issued together so that a thread does not pay
+    // one memory latency per slice (the small-batch layers run this kernel with 8-16 slices on a handful of blocks)
+    for (int ks = 0; ks < p.ksplit; ks += 4) {
+      float4 t[4][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(sp + 4 * q);
-        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      for (int u = 0; u < 4; ++u) {
+        const bool on = ks + u < p.ksplit;
+        const float* sp = src + static_cast<size_t>(on ? ks + u : ks) * slice_stride + c;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[u][q] = on ? __ldcs(reinterpret_cast<const float4*>(sp + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[4 * q] += t[u][q].x; v[4 * q + 1] += t[u][q].y; v[4 * q + 2] += t[u][q].z; v[4 * q + 3] += t[u][q].w;
+        }
     }
     epilogue_32cols(p, v, n_tile * nt + c, b, y, x, nw, plane_stride, rgb0, rgb1, rgb2);
   }

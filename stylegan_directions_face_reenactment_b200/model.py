@@ -351,7 +351,7 @@ class Generator(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == '_workspace' else copy.deepcopy(v, memo)
+            new.__dict__[k] = {} if k in ('_workspace', '_desc_cache') else copy.deepcopy(v, memo)
         return new
 
     # ------------------------------------------------------------------ reference API
@@ -393,6 +393,13 @@ class Generator(nn.Module):
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
         image = self.synthesis(latent, noise)
         return (image, latent) if return_latents else (image, None)
+
+    def enable_cuda_graphs(self, on=True):
+        """Replay the synthesis kernels of no-grad forward calls as one captured CUDA graph per (batch, weights, noise)
+        configuration (also: SGR_CUDA_GRAPHS=1).  Worth it for small batches, where the ~36 launches per frame are bound by
+        the CPU launch rate; weights / noise changes are detected and re-captured.  Off by default."""
+        self._cuda_graphs = bool(on)
+        return self
 
     # ------------------------------------------------------------------ fused synthesis
     def styled_layers(self):

@@ -75,6 +75,38 @@ class NetDescriptor:
         return N.ptr(t)
 
 
+def _signature(g):
+    """(data_ptr, version) of every parameter and buffer the descriptor points at: detects in-place updates (Adam in
+    optimize_g), load_state_dict, .cuda() and re-assignment."""
+    sig = []
+    for t in g.parameters():
+        sig.append(t.data_ptr())
+        sig.append(t._version)
+    for t in g.buffers():
+        sig.append(t.data_ptr())
+        sig.append(t._version)
+    return tuple(sig)
+
+
+def _descriptor(g, noise, batch, backward=False):
+    """NetDescriptor for this call, reused from the previous call when nothing it points at has changed (building it is
+    ~0.25 ms of Python: the dominant cost of a batch-1 frame, which is how run_inference.py drives the generator)."""
+    if any(n is None for n in noise):                  # randomize_noise: fresh tensors every call
+        return NetDescriptor(g, noise, batch, backward)
+    key = (batch, backward, N.default_format(), N.single_pass(), tuple((n.data_ptr(), n._version, tuple(n.shape)) for n in noise))
+    sig = _signature(g)
+    cache = g.__dict__.setdefault('_desc_cache', {})
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    desc = NetDescriptor(g, noise, batch, backward)
+    desc.keep.extend(noise)                            # the cached struct points at them
+    if len(cache) >= 8:
+        cache.clear()
+    cache[key] = (sig, desc)
+    return desc
+
+
 def _workspace(g, desc, batch, device, backward=False):
     key = (batch, device.index, backward)
     ws = g._workspace.get(key)
@@ -90,6 +122,45 @@ def _workspace(g, desc, batch, device, backward=False):
     return ws
 
 
+def _graphs_enabled(g):
+    v = g.__dict__.get('_cuda_graphs')
+    if v is None:
+        import os
+        v = os.environ.get('SGR_CUDA_GRAPHS', '0') not in ('0', '', 'false', 'False')
+    return bool(v)
+
+
+class _GraphedForward:
+    """One captured CUDA graph of sgr_synthesis_forward for a fixed (descriptor, batch): static latent / image buffers,
+    replayed with one launch.  A batch-1 frame is ~36 kernel launches of 5-30 us each, i.e. bound by the CPU launch rate
+    (0.6 ms per frame eager); the graph removes that (run_inference.py renders one frame per generator call)."""
+
+    def __init__(self, g, desc, ws, batch, dev):
+        self.desc, self.ws = desc, ws                         # keep every captured pointer alive
+        self.latent = torch.empty(batch, g.n_latent, g.style_dim, device=dev, dtype=torch.float32)
+        self.image = torch.empty(batch, 3, g.size, g.size, device=dev, dtype=torch.float32)
+        self.graph = torch.cuda.CUDAGraph()
+        lib = N.lib()
+
+        def call():
+            N.check(lib.sgr_synthesis_forward(C.byref(desc.struct), N.ptr(self.latent), batch, N.ptr(self.image), N.ptr(ws),
+                                              ws.numel(), None, N.stream()), 'sgr_synthesis_forward')
+        self.latent.zero_()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                         # warm-up outside capture (one-time attribute calls, packing)
+            call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(self.graph):
+            call()
+
+    def run(self, lat):
+        self.latent.copy_(lat)
+        self.graph.replay()
+        return self.image.clone()                             # callers own their frames (the reference returns fresh tensors)
+
+
 def synthesis_forward(g, latent, noise, want_feats):
     if not latent.is_cuda:
         raise RuntimeError('Generator: latent must be a CUDA tensor (libsgr has no CPU fallback)')
@@ -99,8 +170,14 @@ def synthesis_forward(g, latent, noise, want_feats):
     batch = lat.shape[0]
     dev = lat.device
     with torch.cuda.device(dev):
-        desc = NetDescriptor(g, noise, batch)
+        desc = _descriptor(g, noise, batch)
         ws = _workspace(g, desc, batch, dev)
+        if (not want_feats and _graphs_enabled(g) and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing()
+                and all(n is not None for n in noise)):
+            gf = desc.__dict__.get('graphed')                 # lives and dies with the cached descriptor
+            if gf is None or gf.ws is not ws:
+                gf = desc.__dict__['graphed'] = _GraphedForward(g, desc, ws, batch, dev)
+            return gf.run(lat), None, lat, desc.noise_used
         image = torch.empty(batch, 3, g.size, g.size, device=dev, dtype=torch.float32)
         feats, feat_ptrs = None, None
         if want_feats:

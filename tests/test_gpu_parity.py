@@ -429,3 +429,39 @@ def test_frames_to_uint8_output_stage(pkg):
     refp = orc.frames_to_uint8(x, size=16)
     dp = np.abs(yp.astype(np.int32) - refp.astype(np.int32))
     assert yp.shape == (3, 16, 16, 3) and dp.max() <= 1 and (dp != 0).mean() < 2e-2
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates(pkg):
+    """enable_cuda_graphs(): bit-identical frames to the eager launches, fresh output tensors, re-capture after an in-place
+    weight update (what optimize_g does) and for a new batch size."""
+    size, cm = 32, 2
+    sd = orc.seeded_state_dict(size, cm, seed=8)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    w1 = orc.seeded_wplus(sd, 1, G.n_latent, seed=3).cuda()
+    w2 = orc.seeded_wplus(sd, 1, G.n_latent, seed=4).cuda()
+    with torch.no_grad():
+        e1, e2 = G([w1], input_is_latent=True)[0], G([w2], input_is_latent=True)[0]
+        G.enable_cuda_graphs(True)
+        g1 = G([w1], input_is_latent=True)[0]
+        g2 = G([w2], input_is_latent=True)[0]
+        g1b = G([w1], input_is_latent=True)[0]
+        assert torch.equal(g1, e1) and torch.equal(g2, e2) and torch.equal(g1b, e1)
+        assert g1.data_ptr() != g1b.data_ptr()                      # callers own their frames
+        G.convs[2].conv.weight.mul_(1.25)
+        g3 = G([w1], input_is_latent=True)[0]
+        G.enable_cuda_graphs(False)
+        e3 = G([w1], input_is_latent=True)[0]
+        assert torch.equal(g3, e3) and not torch.equal(g3, e1)
+        G.enable_cuda_graphs(True)
+        w3 = orc.seeded_wplus(sd, 3, G.n_latent, seed=5).cuda()
+        g4 = G([w3], input_is_latent=True)[0]
+        G.enable_cuda_graphs(False)
+        assert torch.equal(g4, G([w3], input_is_latent=True)[0])
+    # autograd calls never go through the graph
+    G.enable_cuda_graphs(True)
+    wg = w1.clone().requires_grad_(True)
+    img, _ = G([wg], input_is_latent=True)
+    img.sum().backward()
+    assert wg.grad is not None and torch.isfinite(wg.grad).all()
