@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -263,7 +263,6 @@ def main():
     lib.sgr_reset_launch_count()
     ms = timed(step_resident, args.steps)
     launches = lib.sgr_launch_count()
-    clocks = sampler.stop() if rank == 0 else None
     frames = BATCH * world * args.steps
     value = frames / (ms * 1e-3)
 
@@ -294,6 +293,7 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps, finish_e2e)
     e2e_value = frames / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed regions
 
     # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch)
     roofline, layers = None, None
