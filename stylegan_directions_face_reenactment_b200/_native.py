@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsgr.so')
+LIB_PATH = os.environ.get('SGR_LIB') or os.path.join(_HERE, 'libsgr.so')     # SGR_LIB: A/B experiments only
 
 MAX_STYLED = 24
 MAX_RGB = 12
