@@ -80,7 +80,7 @@ __device__ __forceinline__ void epilogue_32cols(const ConvKernelParams& p, float
         for (int e = 0; e < 4; ++e)
           split2(v[8 * q + 2 * e] * g[2 * e], v[8 * q + 2 * e + 1] * g[2 * e + 1], p.out_fmt, hi[e], lo[e]);
         *reinterpret_cast<uint4*>(optr + q * chunk_stride) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(optr + plane_stride + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (!p.single_out) *reinterpret_cast<uint4*>(optr + plane_stride + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
 }

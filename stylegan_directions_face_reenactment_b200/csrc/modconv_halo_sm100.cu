@@ -104,17 +104,20 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
         const int b = m / p.tiles_y;
         const int x0 = tx * Cfg::kTileW - 1, y0 = ty * Cfg::kTileH - 1;
         const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(n_tile) * 9 * p.kchunks * (NT * 64);
+        // single-pass mode: hi plane of the halo box; hi half of plane-major weight slabs (NT > 64)
+        const uint32_t a_bytes = p.single ? Cfg::kABytes / 2 : Cfg::kABytes;
+        const uint32_t b_bytes = (p.single && !Cfg::kConcat) ? Cfg::kBBytes / 2 : Cfg::kBBytes;
         const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
           mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
-          mbar_expect_tx(&a_full[as], Cfg::kABytes);
+          mbar_expect_tx(&a_full[as], a_bytes);
           tma_load_5d(a_base + as * Cfg::kABytes, &tmap, &a_full[as], x0 * 8, y0, b, kb * 4, 0);
           for (int tap = 0; tap < 9; ++tap, ++bi) {
             const uint32_t bs = bi % BS;
             mbar_wait(&b_empty[bs], ((bi / BS) & 1) ^ 1);
-            mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
-            bulk_g2s(b_base + bs * Cfg::kBBytes, wsrc + static_cast<size_t>(tap * p.kchunks + kb) * (NT * 64), Cfg::kBBytes,
+            mbar_expect_tx(&b_full[bs], b_bytes);
+            bulk_g2s(b_base + bs * Cfg::kBBytes, wsrc + static_cast<size_t>(tap * p.kchunks + kb) * (NT * 64), b_bytes,
                      &b_full[bs]);
           }
         }
@@ -286,7 +289,7 @@ int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t
   p.nt = nt;
   set_ksplit(&p, choose_ksplit(a, p.m_tiles * p.n_tiles, p.kchunks, 2, static_cast<size_t>(mt) * kTileM * nt * 4));
   CUtensorMap tmap;
-  if (make_act_tensor_map(&tmap, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw + 2, p.bh + 2, 1)) return 1;
+  if (make_act_tensor_map(&tmap, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw + 2, p.bh + 2, 1, p.single ? 1 : 2)) return 1;
   int rc;
   switch (nt) {
     case 256: rc = launch_halo<256, 1>(p, tmap, sms, stream); break;

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
+      const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * (p.single ? 64u : 128u);   // single pass: hi plane only
+      const uint32_t b_row = p.single ? 64u : 128u;                                       // slabs are plane-major: hi half first
       uint32_t g = 0;                                  // running channel-block counter: ring slots and phases
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile / p.m_tiles;
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
             mbar_expect_tx(&a_full[sft], a_bytes);
             tma_load_5d(a_base + sft * kABytes, &tmap, &a_full[sft], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
             mbar_wait(&b_empty[bs], b_par);
-            mbar_expect_tx(&b_full[bs], n_s * 128);
-            bulk_g2s(bdst + prefix * 128, wkc + prefix * 128, n_s * 128, &b_full[bs]);
+            mbar_expect_tx(&b_full[bs], n_s * b_row);
+            bulk_g2s(bdst + prefix * 128, wkc + prefix * 128, n_s * b_row, &b_full[bs]);
           }
         }
       }

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         const int ks = tile % p.ksplit;
         const TileCoord tc = decode_tile(p, tile / p.ksplit);
         const int x0 = tc.tx * p.bw, y0 = tc.ty * p.bh, b0 = tc.tb * p.bb;
-        const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * 128u;
+        // single-pass mode reads only the hi plane of the activations and (plane-major slabs, NT > 64) of the weights
+        const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * (p.single ? 64u : 128u);
+        const uint32_t b_bytes = (p.single && NT > 64) ? Cfg::kBBytes / 2 : Cfg::kBBytes;
         const __nv_bfloat16* wsrc = p.wpacked + static_cast<size_t>(tc.n_tile) * k_iters * (NT * 64);
         const int k0 = ks * k_iters / p.ksplit, k1 = (ks + 1) * k_iters / p.ksplit;
         int tap = k0 / p.kchunks, kc = k0 - tap * p.kchunks;
@@ -116,9 +118,9 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = stage_base + s * Cfg::kStageBytes;
-          mbar_expect_tx(&full[s], a_bytes + Cfg::kBBytes);
+          mbar_expect_tx(&full[s], a_bytes + b_bytes);
           tma_load_5d(sa, &tmap, &full[s], (x0 + dx) * 8, y0 + dy, b0, p.tap_chunk[tap] + kc * 4, 0);
-          bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(k) * (NT * 64), Cfg::kBBytes, &full[s]);
+          bulk_g2s(sa + kABytes, wsrc + static_cast<size_t>(k) * (NT * 64), b_bytes, &full[s]);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
         }
       }
@@ -277,7 +279,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb) {
+                        int bb, int planes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -289,7 +291,7 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
   const cuuint64_t strides[4] = {static_cast<cuuint64_t>(w) * 16, chunk_bytes * (channels / 8), chunk_bytes,
                                  chunk_bytes * (channels / 8) * batch};
   const cuuint32_t box[5] = {static_cast<cuuint32_t>(bw * 8), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bb),
-                             kBlockK / 8, 2};
+                             kBlockK / 8, static_cast<cuuint32_t>(planes)};   // planes == 1: the hi plane only
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -485,6 +487,7 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
   }
   p->fmt = a->operand_format;
   p->single = a->single_pass ? 1 : 0;
+  p->single_out = a->single_pass ? 1 : 0;
   p->acc_base = 1.f / (act_scale(a->operand_format) * w_scale(a->operand_format));
   p->acc_scale = p->acc_base;
   p->ksplit = 1;

@@ -242,9 +242,11 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
   }
   CUtensorMap tmap;
   if (args->up == 3) {       // gather adjoint: the operand is the 4-plane tensor on the (h+1) x (w+1) grid
-    if (make_act_tensor_map(&tmap, args->x_c8, args->batch, 4 * args->cin, args->h_in + 1, args->w_in + 1, p.bw, p.bh, p.bb))
+    if (make_act_tensor_map(&tmap, args->x_c8, args->batch, 4 * args->cin, args->h_in + 1, args->w_in + 1, p.bw, p.bh, p.bb,
+                            p.single ? 1 : 2))
       return 1;
-  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb)) {
+  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb,
+                                 p.single ? 1 : 2)) {
     return 1;
   }
   if (args->up != 2)

@@ -51,7 +51,9 @@ struct ConvKernelParams {
   int act;
   float act_gain;
   int fmt;                      // operand format of x_c8 / wpacked (SGR_FMT_*)
-  int single;                   // 1: hi x hi products only (plain bf16/fp16 tensor-core precision, 1 MMA instead of 3)
+  int single;                   // 1: hi x hi products only (plain bf16/fp16 tensor-core precision, 1 MMA instead of 3);
+                                //    only the hi plane of x_c8 / hi half of the weight slabs is loaded
+  int single_out;               // 1: out_c8 consumers are single-pass too: the lo plane is not written
   float acc_scale;              // undoes the operand scales on the accumulator
   int out_fmt;                  // format of out_c8
   float out_scale;              // activation scale of out_fmt
@@ -81,7 +83,7 @@ struct ConvKernelParams {
 int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // host: build the 5-D tensor map over C8 activation planes
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb);
+                        int bb, int planes = 2);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
 // modconv_scatter_sm100.cu: scatter-form upsampling convolution (parity planes -> p.t_out)
 int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);

@@ -32,6 +32,7 @@ struct UpFinishParams {
   float out_scale;
   __nv_bfloat16* out_c8;       // [2][B][C/8][2H][2W][8] or NULL
   float* out_f32;              // [B,C,2H,2W] or NULL
+  int single_out;              // single-pass consumers: the lo plane is not written
   int strips;                  // column strips of 14 output-producing columns
   int rows;                    // input rows walked by one warp
 };
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams 
           const uint4 h4 = half ? make_uint4(rh[0], rh[1], hi[1][0], hi[1][1]) : make_uint4(hi[0][0], hi[0][1], rh[0], rh[1]);
           const uint4 l4 = half ? make_uint4(rl[0], rl[1], lo[1][0], lo[1][1]) : make_uint4(lo[0][0], lo[0][1], rl[0], rl[1]);
           *reinterpret_cast<uint4*>(o_c8) = h4;
-          *reinterpret_cast<uint4*>(o_c8 + out_plane) = l4;
+          if (!p.single_out) *reinterpret_cast<uint4*>(o_c8 + out_plane) = l4;
         }
         o_c8 += static_cast<size_t>(Wo) * 8;
       }
@@ -289,6 +290,7 @@ int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap
   p.out_scale = act_scale(a->out_format);
   p.out_c8 = static_cast<__nv_bfloat16*>(a->out_c8);
   p.out_f32 = a->out_f32;
+  p.single_out = a->single_pass ? 1 : 0;
   p.strips = (a->w_in + 13) / 14;
   // rows per warp: long strips amortise the two preloaded window rows, short ones keep small layers parallel
   int rows = a->h_in >= 64 ? 16 : (a->h_in >= 32 ? 8 : (a->h_in >= 8 ? 4 : 2));
