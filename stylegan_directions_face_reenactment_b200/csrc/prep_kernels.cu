@@ -214,10 +214,12 @@ __global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int ba
   if (o0 >= j.cout) return;
   const int b0 = blockIdx.z * 32;
   const int nb = min(32, batch - b0);
-  for (int idx = threadIdx.x; idx < 32 * j.cin; idx += blockDim.x) {
-    const int b = idx / j.cin, i = idx - b * j.cin;
-    const float v = b < nb ? __ldg(j.s + static_cast<size_t>(b0 + b) * j.cin + i) : 0.f;
-    s2[idx] = v * v;
+  for (int i = threadIdx.x; i < j.cin; i += blockDim.x) {           // no integer division: column i, all samples
+#pragma unroll 8
+    for (int b = 0; b < 32; ++b) {
+      const float v = b < nb ? __ldg(j.s + static_cast<size_t>(b0 + b) * j.cin + i) : 0.f;
+      s2[b * j.cin + i] = v * v;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -225,13 +225,13 @@ __global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, int slots, 
   __shared__ float sk[16];
   if (threadIdx.x < 16) sk[threadIdx.x] = fir ? fir[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)] : 0.f;
   __syncthreads();
-  const long long total4 = static_cast<long long>(planes) * H * (W / 4);
+  // grid: (x groups of 4 pixels, y, plane) - no integer divisions in the kernel
   const int h2 = H / 2, w2 = W / 2;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total4;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x0 = static_cast<int>(idx % (W / 4)) * 4;
-    const int y = static_cast<int>((idx / (W / 4)) % H);
-    const int pl = static_cast<int>(idx / (static_cast<long long>(W / 4) * H));
+  const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xg >= W / 4) return;
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const int x0 = xg * 4;
+    const int y = blockIdx.y;
     const float b = __ldg(bias + pl % 3);
     float4 a = __ldg(reinterpret_cast<const float4*>(rgb_acc + (static_cast<size_t>(pl) * H + y) * W + x0));
     for (int s = 1; s < slots; ++s) {           // per-column-tile partial sums, fixed order
@@ -264,10 +264,14 @@ __global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, int slots, 
 
 int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
                       float* out, int batch, int H, int W, cudaStream_t st) {
-  const long long total4 = static_cast<long long>(batch) * 3 * H * (W / 4);
-  const long long blocks = (total4 + 255) / 256;
-  torgb_tail_kernel<<<static_cast<unsigned>(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      rgb_acc, slots, bias, skip_in, fir, out, batch * 3, H, W);
+  if (W % 4 != 0 || H > 65535) {
+    set_error("torgb_tail: unsupported image size %dx%d", H, W);
+    return 1;
+  }
+  const int threads = W / 4 >= 128 ? 128 : (W / 4 >= 64 ? 64 : 32);
+  const int planes = batch * 3;
+  dim3 grid((W / 4 + threads - 1) / threads, H, planes < 65535 ? planes : 65535);
+  torgb_tail_kernel<<<grid, threads, 0, st>>>(rgb_acc, slots, bias, skip_in, fir, out, planes, H, W);
   count_launch();
   return check_launch("torgb_tail_kernel") ? 0 : 1;
 }
