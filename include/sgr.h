@@ -207,10 +207,26 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
  * feats: the n_styled saved StyledConv outputs of the forward call (all required).  Replaces ATen autograd through
  * F.conv2d / F.conv_transpose2d and the modulation graph (model.py:232-273) for the A-matrix training step
  * (libs/trainer.py:177-189); generator weight gradients are not produced. */
+/* Optional extra outputs of the backward pass: what a caller needs to assemble the gradients of the GENERATOR's own
+ * parameters (optimize_g, libs/optimization.py:25-72).  Any pointer (array or entry) may be NULL.
+ *   gfeats[l]     [B,cout_l,res,res]  dL/d(output of StyledConv l)                       (n_styled entries)
+ *   ds_styled[l]  [B,cin_l]           dL/d(style s_l), convolution + demodulation terms  (n_styled entries)
+ *   ds_rgb[r]     [B,cin_r]           dL/d(style of ToRGB r)                             (n_rgb entries)
+ *   g_input       [B,cin_0,4,4]       dL/d(const_input * s_0), the modulated input of conv1 */
+typedef struct sgr_backward_extras {
+  float* const* gfeats;
+  float* const* ds_styled;
+  float* const* ds_rgb;
+  float* g_input;
+} sgr_backward_extras;
+
 size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch);
 int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
                            const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
                            void* stream);
+int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
+                              const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
+                              const sgr_backward_extras* extras, void* stream);
 
 #ifdef __cplusplus
 }

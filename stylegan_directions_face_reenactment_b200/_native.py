@@ -50,6 +50,10 @@ class RgbLayer(C.Structure):
                 ('bias', _fp), ('fir', _fp), ('fir_flipped', _fp)]
 
 
+class BackwardExtras(C.Structure):
+    _fields_ = [('gfeats', C.POINTER(_fp)), ('ds_styled', C.POINTER(_fp)), ('ds_rgb', C.POINTER(_fp)), ('g_input', _fp)]
+
+
 class Synthesis(C.Structure):
     _fields_ = [('size', C.c_int), ('n_styled', C.c_int), ('n_rgb', C.c_int), ('n_latent', C.c_int), ('format', C.c_int),
                 ('single_pass', C.c_int), ('const_input', _fp), ('styled', StyledLayer * MAX_STYLED), ('rgb', RgbLayer * MAX_RGB)]
@@ -80,6 +84,8 @@ SIGNATURES = {
     'sgr_synthesis_backward_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
     'sgr_synthesis_backward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, C.c_size_t,
                                          _fp]),
+    'sgr_synthesis_backward_ex': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, C.c_size_t,
+                                            C.POINTER(BackwardExtras), _fp]),
     'sgr_synthesis_forward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, _fp, _fp, C.c_size_t, C.POINTER(_fp),
                                         _fp]),
 }

@@ -32,6 +32,7 @@ struct BwdActParams {
   long long noise_bstride;
   const float* noise_w;
   __nv_bfloat16* out_c8;  // gz planes or NULL
+  float* out_ga;          // dL/d(a) [B,C,H,W] fp32 (generator-parameter gradients) or NULL
   float* out_gz4;         // gz as fp32 [B][C/4][H][W][4] (scatter-form up layers: input of up_bwd_prepare_kernel) or NULL
   int s2d;
   int act;                // 0: constant-input pseudo layer (only the ds reduction)
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
         ga = fmaf(r, sr[e], ga);
         dsr[e] = fmaf(a, r, dsr[e]);
       }
+      if (p.out_ga) p.out_ga[(static_cast<size_t>(b) * p.C + c0 + e) * HW + pix] = ga;
       gzv[e] = 0.f;
       if (p.act) {
         const bool pos = a > 0.f;
@@ -395,6 +397,12 @@ size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batc
 int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
                            const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
                            void* stream) {
+  return sgr_synthesis_backward_ex(net, latent, batch, feats, grad_image, dlatent, workspace, workspace_bytes, nullptr, stream);
+}
+
+int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,
+                              const float* grad_image, float* dlatent, void* workspace, size_t workspace_bytes,
+                              const sgr_backward_extras* extras, void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
@@ -491,6 +499,7 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     p.noise = Ly.noise;
     p.noise_bstride = Ly.noise_batch_stride;
     p.noise_w = Ly.noise_weight;
+    if (extras && extras->gfeats) p.out_ga = extras->gfeats[l];
     const bool scatter = Ly.up == 2;      // gather adjoint: FIR^T to parity planes, then the 9 real taps
     if (scatter) p.out_gz4 = F(pl.gz_off);
     else p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
@@ -539,6 +548,12 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
     gx_next = F(pl.gx_off[gx_cur]);
     gx_cur = 1 - gx_cur;
   }
+  if (extras && extras->g_input && gx_next &&
+      cudaMemcpyAsync(extras->g_input, gx_next, static_cast<size_t>(batch) * net->styled[0].cin * 16 * 4, cudaMemcpyDeviceToDevice,
+                      st) != cudaSuccess) {
+    set_error("synthesis_backward: copy of g_input failed");
+    return 1;
+  }
   // conv term of ds_0: the input of conv1 is the constant 4x4 tensor (batch stride 0)
   {
     BwdActParams p;
@@ -569,6 +584,22 @@ int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int ba
   ds_finish_kernel<<<dim3((cin_max + 127) / 128, batch, L), 128, 0, st>>>(dj);
   count_launch();
   if (!check_launch("ds_finish_kernel")) return 1;
+  if (extras) {
+    for (int l = 0; l < L; ++l)
+      if (extras->ds_styled && extras->ds_styled[l] &&
+          cudaMemcpyAsync(extras->ds_styled[l], F(pl.ds_off[l]), static_cast<size_t>(batch) * net->styled[l].cin * 4,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("synthesis_backward: copy of ds failed");
+        return 1;
+      }
+    for (int r = 0; r < R; ++r)
+      if (extras->ds_rgb && extras->ds_rgb[r] &&
+          cudaMemcpyAsync(extras->ds_rgb[r], F(pl.dsrgb_off[r]), static_cast<size_t>(batch) * net->rgb[r].cin * 4,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("synthesis_backward: copy of ds_rgb failed");
+        return 1;
+      }
+  }
   LatJobs lj;
   lj.n = 0;
   for (int l = 0; l < L; ++l)

@@ -195,13 +195,16 @@ def synthesis_forward(g, latent, noise, want_feats):
 
 
 class _Synthesis(torch.autograd.Function):
-    """Autograd node for dL/d(latent) — the only gradient the A-matrix training consumes (libs/trainer.py:144,187-189)."""
+    """Autograd node for dL/d(latent) — the only gradient the A-matrix training consumes (libs/trainer.py:144,187-189) —
+    and, in train() mode, for the generator's own parameters (optimize_g, libs/optimization.py:25-72): those enter as
+    extra inputs so that autograd routes their gradients (backward.py)."""
 
     @staticmethod
-    def forward(ctx, latent, g, noise):
+    def forward(ctx, latent, g, noise, *params):
         image, feats, lat, noise_used = synthesis_forward(g, latent, noise, want_feats=True)
         ctx.g = g
         ctx.noise = noise_used
+        ctx.n_params = len(params)
         ctx.save_for_backward(lat, *feats)
         return image
 
@@ -209,14 +212,33 @@ class _Synthesis(torch.autograd.Function):
     def backward(ctx, grad_image):
         from .backward import synthesis_backward
         lat, *feats = ctx.saved_tensors
-        return synthesis_backward(ctx.g, lat, feats, ctx.noise, grad_image), None, None
+        want = ctx.n_params > 0 and any(ctx.needs_input_grad[3:])
+        dlat, pgrads = synthesis_backward(ctx.g, lat, feats, ctx.noise, grad_image, want_param_grads=want)
+        if not ctx.needs_input_grad[0]:
+            dlat = None
+        if ctx.n_params == 0:
+            return dlat, None, None
+        if pgrads is None:
+            pgrads = [None] * ctx.n_params
+        pgrads = [pg if need else None for pg, need in zip(pgrads, ctx.needs_input_grad[3:])]
+        return (dlat, None, None) + tuple(pgrads)
 
 
 def run_synthesis(g, latent, noise, return_features=False):
     if return_features:
         image, feats, _, _ = synthesis_forward(g, latent, noise, want_feats=True)
         return image, feats
-    if torch.is_grad_enabled() and latent.requires_grad:
-        return _Synthesis.apply(latent, g, noise)
+    if torch.is_grad_enabled():
+        # train() mode (optimize_g): the generator's parameters are differentiable inputs; eval() mode: frozen generator
+        params = []
+        if g.training:
+            from .backward import synthesis_param_list
+            params = synthesis_param_list(g)
+            if not any(p.requires_grad for p in params):
+                params = []
+            elif any(n is None for n in noise):
+                raise RuntimeError('generator weight gradients need fixed noise buffers (randomize_noise=False)')
+        if latent.requires_grad or params:
+            return _Synthesis.apply(latent, g, noise, *params)
     image, _, _, _ = synthesis_forward(g, latent, noise, want_feats=False)
     return image

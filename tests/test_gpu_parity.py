@@ -465,3 +465,71 @@ def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates(pkg):
     img, _ = G([wg], input_is_latent=True)
     img.sum().backward()
     assert wg.grad is not None and torch.isfinite(wg.grad).all()
+
+
+@pytest.mark.parametrize('size,cm,batch', [(8, 2, 2), (32, 2, 2)])
+def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
+    """SURVEY 8f-1 (optimize_g, libs/optimization.py:25-72): in train() mode every parameter the synthesis path reads gets
+    its gradient (conv / modulation / noise / bias of every StyledConv and ToRGB, the constant input) - against the oracle's
+    autograd.  Tolerance as for dL/dlatent (leaky-relu mask flips): 2e-2 of each tensor's max, cosine >= 0.999."""
+    sd = orc.seeded_state_dict(size, cm, seed=14)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().train()
+    wplus = orc.seeded_wplus(sd, batch, G.n_latent, seed=23)
+    rng = np.random.Generator(np.random.PCG64(5))
+    r = T(rng.standard_normal((batch, 3, size, size), dtype=np.float32))
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'noises.' not in k and '.kernel' not in k else v)
+           for k, v in sd.items()}
+    ref, _ = orc.generator_forward(sdg, [wplus], size, cm, input_is_latent=True)
+    (ref * r).sum().backward()
+    img, _ = G([wplus.cuda()], input_is_latent=True)
+    assert err(img, ref.detach().numpy()) <= 1e-3
+    (img * r.cuda()).sum().backward()
+    checked = 0
+    for name, p in G.named_parameters():
+        if name.startswith('style.'):
+            assert p.grad is None                    # the mapping network is not on the W+ path
+            continue
+        gref = sdg[name].grad
+        assert gref is not None and p.grad is not None, name
+        gr, gg = gref.numpy(), p.grad.cpu().numpy()
+        scale = np.abs(gr).max()
+        assert np.abs(gg - gr).max() <= 2e-2 * max(scale, 1e-6), (name, np.abs(gg - gr).max(), scale)
+        if gr.size > 8:
+            cos = float((gg * gr).sum() / (np.linalg.norm(gg) * np.linalg.norm(gr) + 1e-30))
+            assert cos >= 0.999, (name, cos)
+        checked += 1
+    assert checked == 1 + 5 * G.num_layers + 4 * (G.log_size - 1)
+    # eval() mode: the generator is frozen (A-matrix training): no parameter gradient is formed
+    G.zero_grad(set_to_none=True)
+    G.eval()
+    wg = wplus.cuda().requires_grad_(True)
+    (G([wg], input_is_latent=True)[0] * r.cuda()).sum().backward()
+    assert wg.grad is not None and all(p.grad is None for p in G.parameters())
+
+
+def test_optimize_g_style_finetuning_step_reduces_loss(pkg):
+    """The loop of libs/optimization.py:45-68 in miniature: Adam on convs[4..] parameters lowers an L2 loss to a target."""
+    size, cm = 32, 2
+    sd = orc.seeded_state_dict(size, cm, seed=3)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda()
+    import copy
+    G0 = copy.deepcopy(G).eval()
+    latent = orc.seeded_wplus(sd, 1, G.n_latent, seed=2).cuda()
+    with torch.no_grad():
+        target = G0([latent], input_is_latent=True)[0] * 0.9 + 0.05
+    G.train()
+    params = [p for i in range(2, len(G.convs)) for p in G.convs[i].parameters()]
+    opt = torch.optim.Adam(params, lr=1e-4)          # random-init N(0,1) weights: the reference's 3e-3 is for trained nets
+    losses = []
+    for _ in range(10):
+        img, _ = G([latent], input_is_latent=True)
+        loss = (img - target).pow(2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.9 * losses[0] and all(np.isfinite(losses)), losses
