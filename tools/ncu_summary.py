@@ -56,13 +56,15 @@ def full(src, dst_md, dst_json):
         rd, wr = float(vals[7].replace(',', '')), float(vals[8].replace(',', ''))
         if 'up_finish' in name:
             fin_bytes += (rd + wr) * 1e6
+        elif 'splitk_finish' in name:
+            conv_bytes += (rd + wr) * 1e6        # part of its convolution
         else:
             conv_bytes += (rd + wr) * 1e6
         lines.append('| `%s` | %s | %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |' % (
             name, vals[1], vals[2], float(vals[3]), float(vals[4]), float(vals[5]), float(vals[6]), rd, wr))
     with open(dst_md, 'w') as f:
         f.write('# `ncu --set full` of the conv GEMM + FIR-pass launches of one step (B=32, 256^2, cm=1)\n\n')
-        f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:"modconv|upconv|up_finish" '
+        f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:"modconv|upconv|up_finish|splitk_finish" '
                 '-s <launches of 3 warm-up steps> -c <launches of one step> -o gpurun_out/prof python bench.py --steps 2 '
                 '--warmup 3 --cpu-baseline 0` (the .ncu-rep stays out of git; this table is `ncu -i ... --page raw --csv` '
                 'filtered by tools/ncu_summary.py).  Durations under ncu are cold-cache and serialised.\n\n')
