@@ -148,6 +148,28 @@ typedef struct sgr_conv_args {
 } sgr_conv_args;
 int sgr_modconv_forward(const sgr_conv_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Weight gradient of one modulated 3x3 convolution (the cuDNN wgrad behind ATen autograd of model.py:254,263,269,
+ * needed when the generator itself is trained: optimize_g, libs/optimization.py:25-72) as ONE tensor-core GEMM over all
+ * pixels of all samples, bf16 hi/lo operands (3 MMAs per product), deterministic:
+ *   up == 0:  gw[o,i,ky,kx] = sum_{b,y,x} gz[b,o,y,x] * x[b,i,y+ky-1,x+kx-1]
+ *   up == 2:  gw[o,i,ky,kx] = sum_{b,y,x} G[b,o,2y+ky,2x+kx] * x[b,i,y,x],  G = gradient of the (2h+1)x(2w+1) output of
+ *             conv_transpose2d(stride 2), passed as its four parity planes stacked as channels:
+ *             gz_c8 channel (2*pu+pv)*cout + o at (I,J) = G[o, 2I+pu, 2J+pv] on the (h_in+1) x (w_in+1) grid (0 outside G).
+ * x_c8 is the layer input ALREADY multiplied by the style (what the forward GEMM consumed); both operands are C8 planes
+ * in SGR_FMT_BF16.  gw is the gradient with respect to W_bar = scale * weight[0] before the demodulation term. */
+typedef struct sgr_wgrad_args {
+  int batch, cin, cout, h_in, w_in;
+  int up;                 /* 0 or 2 */
+  const void* x_c8;       /* [2][B][cin/8][h_in][w_in][8] bf16 */
+  const void* gz_c8;      /* up == 0: [2][B][cout/8][h_in][w_in][8]; up == 2: [2][B][4*cout/8][h_in+1][w_in+1][8] */
+  float* gw;              /* [cout,cin,3,3], fully overwritten */
+  void* scratch;          /* >= sgr_wgrad_scratch_bytes(cout, cin): per-slice fp32 partial sums */
+  size_t scratch_bytes;
+} sgr_wgrad_args;
+size_t sgr_wgrad_scratch_bytes(int cout, int cin);
+int sgr_modconv_wgrad(const sgr_wgrad_args* args, void* stream);
+
 /* styles s[b,i] = latent_row[b,:] . mod_weight[i,:] / sqrt(512) + mod_bias[i]   (EqualLinear, model.py:148-157,235)
  * demod d[b,o]  = rsqrt(sum_i s[b,i]^2 wsq[o,i] + 1e-8)                          (model.py:238-240 in the form of §9.1) */
 int sgr_style_affine(const float* latent, int latent_stride, int batch, const float* mod_weight,
@@ -218,6 +240,9 @@ typedef struct sgr_backward_extras {
   float* const* ds_styled;
   float* const* ds_rgb;
   float* g_input;
+  float* const* gw_styled;  /* [cout_l,cin_l,3,3] convolution term of dL/d(W_bar_l), W_bar = scale * weight (n_styled entries):
+                               the tcgen05 weight-gradient GEMM of sgr_modconv_wgrad on the operands the backward pass
+                               already holds; layers packed with up == 1 (non-separable FIR) are left untouched */
 } sgr_backward_extras;
 
 size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch);

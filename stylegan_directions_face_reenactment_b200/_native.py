@@ -51,7 +51,13 @@ class RgbLayer(C.Structure):
 
 
 class BackwardExtras(C.Structure):
-    _fields_ = [('gfeats', C.POINTER(_fp)), ('ds_styled', C.POINTER(_fp)), ('ds_rgb', C.POINTER(_fp)), ('g_input', _fp)]
+    _fields_ = [('gfeats', C.POINTER(_fp)), ('ds_styled', C.POINTER(_fp)), ('ds_rgb', C.POINTER(_fp)), ('g_input', _fp),
+                ('gw_styled', C.POINTER(_fp))]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [('batch', C.c_int), ('cin', C.c_int), ('cout', C.c_int), ('h_in', C.c_int), ('w_in', C.c_int),
+                ('up', C.c_int), ('x_c8', _fp), ('gz_c8', _fp), ('gw', _fp), ('scratch', _fp), ('scratch_bytes', C.c_size_t)]
 
 
 class Synthesis(C.Structure):
@@ -78,6 +84,8 @@ SIGNATURES = {
     'sgr_choose_column_tile': (C.c_int, [C.c_int] * 4),
     'sgr_nchw_to_c8': (C.c_int, [_fp, _fp, _fp] + [C.c_int] * 6 + [_fp]),
     'sgr_modconv_forward': (C.c_int, [C.POINTER(ConvArgs), _fp]),
+    'sgr_wgrad_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'sgr_modconv_wgrad': (C.c_int, [C.POINTER(WgradArgs), _fp]),
     'sgr_style_affine': (C.c_int, [_fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp]),
     'sgr_demod': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     'sgr_synthesis_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -279,7 +279,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb, int planes) {
+                        int bb, int planes, int chunk_box) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -291,7 +291,7 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
   const cuuint64_t strides[4] = {static_cast<cuuint64_t>(w) * 16, chunk_bytes * (channels / 8), chunk_bytes,
                                  chunk_bytes * (channels / 8) * batch};
   const cuuint32_t box[5] = {static_cast<cuuint32_t>(bw * 8), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bb),
-                             kBlockK / 8, static_cast<cuuint32_t>(planes)};   // planes == 1: the hi plane only
+                             static_cast<cuuint32_t>(chunk_box), static_cast<cuuint32_t>(planes)};   // planes == 1: the hi plane only
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

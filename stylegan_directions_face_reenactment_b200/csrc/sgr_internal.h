@@ -83,8 +83,9 @@ struct ConvKernelParams {
 int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // host: build the 5-D tensor map over C8 activation planes
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb, int planes = 2);
+                        int bb, int planes = 2, int chunk_box = kBlockK / 8);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
+int num_sms();
 // modconv_scatter_sm100.cu: scatter-form upsampling convolution (parity planes -> p.t_out)
 int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // modconv_halo_sm100.cu: resident-halo variant for plain 3x3 layers of at least 16x16 pixels
@@ -95,6 +96,10 @@ int choose_ksplit(const sgr_conv_args* a, int tiles, int k_units, int min_units_
 void set_ksplit(ConvKernelParams* p, int ksplit);
 int splitk_finish_launch(const ConvKernelParams& p, cudaStream_t stream);
 int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream);
+
+// wgrad_sm100.cu: weight-gradient GEMM (K = pixels, MN-major operands)
+size_t wgrad_scratch_bytes(int cout, int cin);
+int wgrad_launch(const sgr_wgrad_args* a, cudaStream_t stream);
 
 // prep_kernels.cu
 struct StyleJob {

@@ -1,0 +1,365 @@
+// Weight gradient of the modulated 3x3 convolutions on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the cuDNN wgrad that ATen autograd runs for F.conv2d / F.conv_transpose2d(groups = batch) in
+// ModulatedConv2d.forward (libs/gan/StyleGAN2/model.py:254,263,269) when the generator itself is fine-tuned
+// (optimize_g, libs/optimization.py:25-72).  In the shared-weight form the
+// gradient with respect to W_bar = scale * W is ONE dense contraction over all pixels of all samples:
+//     plain   gW[o,i,ky,kx] = sum_{b,y,x} gz[b,o,y,x] * xs[b,i,y+ky-1,x+kx-1]                       (zero padding)
+//     up      gW[o,i,ky,kx] = sum_{b,y,x} G[b,o,2y+ky,2x+kx] * xs[b,i,y,x]
+// with xs = a_{l-1} * s_l (the modulated input), gz = dL/d(conv output) (demodulation already applied) and, for the
+// upsampling layers, G = FIR^T(gz) on the (2H+1)^2 grid of conv_transpose2d, read through its four parity planes
+// G[2I+pu, 2J+pv] = plane_{2pu+pv}[I,J] — the operand up_bwd_prepare_kernel already builds for the data gradient.
+//
+// GEMM view: D_tap[o, i] = sum_pix A_tap[pix, o] * B[pix, i]  — M = 128 output channels, N = NT input channels,
+// K = pixels.  Both operands are the C8 activation layout [plane(hi,lo)][B][C/8][H][W][8] bf16, i.e. "MN-major" for this
+// GEMM: a TMA box [chunk][y][x][8] lands in shared memory as the canonical no-swizzle MN-major UMMA layout (16 B = 8
+// channels contiguous, 8 consecutive pixels = one 128 B core matrix, channel chunks SBO apart, the second 8-pixel group of
+// a K = 16 step LBO apart), so no transposition pass is needed.  The 3x3 taps are relative shifts between the two
+// operands: the xs tile is loaded unshifted and the gz box carries the halo, a tap is a start-address offset into it.
+// A work item = (tap group, 128-channel row tile, NT-channel column tile, slice of the pixel tiles); a tap group shares
+// one gz box (plain: the three kx of a kernel row; up: the taps of one parity plane) and owns one TMEM accumulator per
+// tap.  Slices write fp32 partials and wgrad_finish_kernel adds them in slice order (deterministic, no atomics).
+// fp32 parity: bf16 hi/lo operands, three MMAs per product, like every other gradient GEMM of the library.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over work items): warp0 TMA producer, warp1 MMA issuer, warp2 TMEM
+// allocator, warps4-7 epilogue (TMEM -> registers -> partial slot).
+#include <algorithm>
+#include <string.h>
+
+#include "sgr_internal.h"
+#include "sgr_ptx.cuh"
+
+namespace sgr {
+
+constexpr int kWgPix = 64;           // pixels (GEMM K) per pipeline stage: bw x bh = 16 x 4 or 8 x 8
+constexpr int kWgMaxStages = 4;
+
+struct WgradGroup {
+  int chunk_base;      // first 8-channel chunk of the gz-side operand (parity plane of an up layer)
+  int ay, ax;          // origin of the gz box relative to the xs tile origin
+  int ntaps;           // <= 4
+  int tap_off[4];      // byte offset of the tap's first pixel inside the gz box
+  int tap_out[4];      // ky * 3 + kx
+};
+
+struct WgradParams {
+  int H, W;                      // xs pixel grid
+  int bw, bh;                    // xs tile
+  int tiles_x, tiles_y, n_ptiles;
+  int o_tiles, i_tiles, nt, cout, cin;
+  int n_groups, slices, stages;
+  uint32_t a_bytes, b_bytes;     // gz box / xs box, both planes
+  uint32_t a_sbo, a_lbo, a_kstep;
+  WgradGroup g[4];
+  float* part;                   // [slices][9][cout][cin]
+};
+
+struct WgItem {
+  int g, ot, it, s, p0, p1;
+};
+__device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
+  WgItem w;
+  w.s = item % p.slices; item /= p.slices;
+  w.it = item % p.i_tiles; item /= p.i_tiles;
+  w.ot = item % p.o_tiles;
+  w.g = item / p.o_tiles;
+  w.p0 = static_cast<int>(static_cast<long long>(w.s) * p.n_ptiles / p.slices);
+  w.p1 = static_cast<int>(static_cast<long long>(w.s + 1) * p.n_ptiles / p.slices);
+  return w;
+}
+
+// idesc of umma_idesc with both operands MN-major (bits 15, 16)
+__device__ __forceinline__ uint32_t wg_idesc(int n) { return umma_idesc(kFmtBF16, kTileM, n) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                       const __grid_constant__ CUtensorMap tmap_b, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kWgMaxStages;
+  uint64_t* tfull = empty + kWgMaxStages;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  uint8_t* stage_base = smem + 1024;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const int S = p.stages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_items = p.n_groups * p.o_tiles * p.i_tiles * p.slices;
+  const int tiles_per_image = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const WgItem w = wg_decode(p, item);
+        const WgradGroup& G = p.g[w.g];
+        for (int pt = w.p0; pt < w.p1; ++pt, ++it) {
+          const int b = pt / tiles_per_image;
+          const int r = pt - b * tiles_per_image;
+          const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+          const int x0 = tx * p.bw, y0 = ty * p.bh;
+          const uint32_t s = it % S;
+          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          uint8_t* sa = stage_base + s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          tma_load_5d(sa, &tmap_a, &full[s], (x0 + G.ax) * 8, y0 + G.ay, b, G.chunk_base + w.ot * 16, 0);
+          tma_load_5d(sa + p.a_bytes, &tmap_b, &full[s], x0 * 8, y0, b, w.it * (p.nt / 8), 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = wg_idesc(p.nt);
+      const uint32_t a_plane = 16 * p.a_sbo;                       // 16 chunks per plane of the gz box
+      const uint32_t b_sbo = kWgPix * 16, b_plane = (p.nt / 8) * b_sbo;
+      uint32_t it = 0, icount = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
+        const WgItem w = wg_decode(p, item);
+        const WgradGroup& G = p.g[w.g];
+        mbar_wait(tempty, (icount & 1) ^ 1);
+        tc_fence_after();
+        for (int pt = w.p0; pt < w.p1; ++pt, ++it) {
+          const uint32_t s = it % S;
+          mbar_wait(&full[s], (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + s * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+#pragma unroll 1
+          for (int t = 0; t < G.ntaps; ++t) {
+            const uint32_t d_tmem = tmem_base + t * p.nt;
+#pragma unroll
+            for (int j = 0; j < kWgPix / 16; ++j) {
+              const uint32_t a_off = a_addr + G.tap_off[t] + j * p.a_kstep;
+              const uint32_t b_off = b_addr + j * 256;
+              const uint64_t a_hi = umma_desc(a_off, p.a_lbo, p.a_sbo);
+              const uint64_t a_lo = umma_desc(a_off + a_plane, p.a_lbo, p.a_sbo);
+              const uint64_t b_hi = umma_desc(b_off, 128, b_sbo);
+              const uint64_t b_lo = umma_desc(b_off + b_plane, 128, b_sbo);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, (pt > w.p0 || j > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int ew = warp - 4;
+    uint32_t icount = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
+      const WgItem w = wg_decode(p, item);
+      const WgradGroup& G = p.g[w.g];
+      const int o = w.ot * kTileM + ew * 32 + lane;
+      mbar_wait(tfull, icount & 1);
+      tc_fence_after();
+      for (int t = 0; t < G.ntaps; ++t) {
+        float* dst = p.part + ((static_cast<size_t>(w.s) * 9 + G.tap_out[t]) * p.cout + o) * p.cin + w.it * p.nt;
+#pragma unroll 1
+        for (int c = 0; c < p.nt; c += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + t * p.nt + c, v);
+          tmem_ld_wait();
+          if (o < p.cout) {
+            float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// gw[o][i][tap] = sum_s part[s][tap][o][i], slices in order
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ part, int slices, int cout, int cin,
+                                                           float* __restrict__ gw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * cin) return;
+  const size_t tap_stride = static_cast<size_t>(cout) * cin;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int s = 0; s < slices; ++s) {
+    const float* src = part + static_cast<size_t>(s) * 9 * tap_stride + idx;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] += __ldcs(src + t * tap_stride);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) gw[static_cast<size_t>(idx) * 9 + t] = acc[t];
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int wgrad_slices(int sms, int base_items, int n_ptiles, int cout, int cin, size_t scratch_bytes) {
+  int s = (2 * sms + base_items - 1) / base_items;
+  s = std::max(1, std::min(std::min(s, 128), n_ptiles));
+  const size_t per_slice = static_cast<size_t>(9) * cout * cin * 4;
+  const size_t cap = scratch_bytes / per_slice;
+  if (cap < 1) return 0;
+  if (static_cast<size_t>(s) > cap) s = static_cast<int>(cap);
+  return s;
+}
+
+size_t wgrad_scratch_bytes(int cout, int cin) {
+  // enough slices for 2 x 148 work items (at most 128 slices; 66 MB on a 512 -> 512 layer)
+  const size_t per_slice = static_cast<size_t>(9) * cout * cin * 4;
+  const int base = 3 * ((cout + 127) / 128) * std::max(1, cin / 128);
+  const int s = std::max(1, std::min(128, (2 * 148 + base - 1) / base));
+  return per_slice * s;
+}
+
+int wgrad_launch(const sgr_wgrad_args* a, cudaStream_t stream) {
+  const int sms = num_sms();
+  if (sms <= 0) {
+    set_error("modconv_wgrad: no CUDA device");
+    return 1;
+  }
+  if (!a->x_c8 || !a->gz_c8 || !a->gw || !a->scratch || a->batch <= 0 || a->cin < 32 || a->cin % 32 || a->cout < 8 ||
+      a->cout % 8 || (a->up != 0 && a->up != 2) || a->h_in <= 0 || a->w_in <= 0) {
+    set_error("modconv_wgrad: bad arguments (cin %d, cout %d, up %d)", a->cin, a->cout, a->up);
+    return 1;
+  }
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = a->h_in; p.W = a->w_in;
+  p.bw = a->w_in > 8 ? 16 : 8;
+  p.bh = kWgPix / p.bw;
+  p.tiles_x = (a->w_in + p.bw - 1) / p.bw;
+  p.tiles_y = (a->h_in + p.bh - 1) / p.bh;
+  p.n_ptiles = a->batch * p.tiles_x * p.tiles_y;
+  p.cout = a->cout; p.cin = a->cin;
+  p.nt = std::min(a->cin, 128);
+  if (a->cin % p.nt) {
+    set_error("modconv_wgrad: cin %d is not a multiple of the column tile %d", a->cin, p.nt);
+    return 1;
+  }
+  p.o_tiles = (a->cout + kTileM - 1) / kTileM;
+  p.i_tiles = a->cin / p.nt;
+  const int abw = a->up ? p.bw + 1 : p.bw + 2, abh = a->up ? p.bh + 1 : p.bh;
+  p.a_sbo = static_cast<uint32_t>(abw) * abh * 16;
+  p.a_bytes = 2 * 16 * p.a_sbo;
+  p.b_bytes = 2 * static_cast<uint32_t>(p.nt / 8) * kWgPix * 16;
+  p.a_lbo = p.bw == 16 ? 128 : static_cast<uint32_t>(abw) * 16;
+  p.a_kstep = (p.bw == 16 ? 1 : 2) * static_cast<uint32_t>(abw) * 16;
+  if (!a->up) {
+    p.n_groups = 3;                                  // one kernel row per group: gz box rows y0 + 1 - ky .., columns x0 - 1 ..
+    for (int ky = 0; ky < 3; ++ky) {
+      WgradGroup& G = p.g[ky];
+      G.chunk_base = 0; G.ay = 1 - ky; G.ax = -1; G.ntaps = 3;
+      for (int kx = 0; kx < 3; ++kx) {
+        G.tap_off[kx] = (2 - kx) * 16;
+        G.tap_out[kx] = ky * 3 + kx;
+      }
+    }
+  } else {
+    p.n_groups = 4;                                  // one parity plane per group, heaviest (ee, 4 taps) first
+    for (int pl = 0; pl < 4; ++pl) {
+      WgradGroup& G = p.g[pl];
+      const int pu = pl >> 1, pv = pl & 1;
+      G.chunk_base = pl * (a->cout / 8); G.ay = 0; G.ax = 0; G.ntaps = 0;
+      for (int ky = pu; ky < 3; ky += 2)
+        for (int kx = pv; kx < 3; kx += 2) {
+          G.tap_off[G.ntaps] = ((ky == 2 ? abw : 0) + (kx == 2 ? 1 : 0)) * 16;
+          G.tap_out[G.ntaps] = ky * 3 + kx;
+          ++G.ntaps;
+        }
+    }
+  }
+  const int base_items = p.n_groups * p.o_tiles * p.i_tiles;
+  p.slices = wgrad_slices(sms, base_items, p.n_ptiles, a->cout, a->cin, a->scratch_bytes);
+  if (p.slices < 1) {
+    set_error("modconv_wgrad: scratch too small (%zu bytes, one slice needs %zu)", a->scratch_bytes,
+              static_cast<size_t>(9) * a->cout * a->cin * 4);
+    return 1;
+  }
+  p.part = static_cast<float*>(a->scratch);
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  const int max_smem = 227 * 1024;
+  p.stages = std::min<int>(kWgMaxStages, (max_smem - 1024) / stage_bytes);
+  if (p.stages < 2) {
+    set_error("modconv_wgrad: pipeline stage of %u bytes does not fit twice", stage_bytes);
+    return 1;
+  }
+  const int smem_bytes = 1024 + p.stages * stage_bytes;
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) {
+      set_error("modconv_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = max_smem;
+  }
+  CUtensorMap tmap_a, tmap_b;
+  const int a_ch = a->up ? 4 * a->cout : a->cout, a_h = a->up ? a->h_in + 1 : a->h_in, a_w = a->up ? a->w_in + 1 : a->w_in;
+  if (make_act_tensor_map(&tmap_a, a->gz_c8, a->batch, a_ch, a_h, a_w, abw, abh, 1, 2, 16)) return 1;
+  if (make_act_tensor_map(&tmap_b, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw, p.bh, 1, 2, p.nt / 8)) return 1;
+  const int total_items = base_items * p.slices;
+  wgrad_kernel<<<std::min(total_items, sms), 256, smem_bytes, stream>>>(tmap_a, tmap_b, p);
+  count_launch();
+  if (!check_launch("wgrad_kernel")) return 1;
+  wgrad_finish_kernel<<<(a->cout * a->cin + 255) / 256, 256, 0, stream>>>(p.part, p.slices, a->cout, a->cin, a->gw);
+  count_launch();
+  return check_launch("wgrad_finish_kernel") ? 0 : 1;
+}
+
+}  // namespace sgr
+
+using namespace sgr;
+
+extern "C" {
+
+size_t sgr_wgrad_scratch_bytes(int cout, int cin) { return wgrad_scratch_bytes(cout, cin); }
+
+int sgr_modconv_wgrad(const sgr_wgrad_args* args, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: libsgr has no CPU fallback");
+    return 1;
+  }
+  if (!args) {
+    set_error("modconv_wgrad: null arguments");
+    return 1;
+  }
+  return wgrad_launch(args, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
