@@ -240,10 +240,36 @@ typedef struct sgr_backward_extras {
   float* const* ds_styled;
   float* const* ds_rgb;
   float* g_input;
-  float* const* gw_styled;  /* [cout_l,cin_l,3,3] convolution term of dL/d(W_bar_l), W_bar = scale * weight (n_styled entries):
-                               the tcgen05 weight-gradient GEMM of sgr_modconv_wgrad on the operands the backward pass
-                               already holds; layers packed with up == 1 (non-separable FIR) are left untouched */
+  const struct sgr_param_grads* params;  /* NULL, or where to write the gradient of every generator parameter (below) */
+  void* wgrad_scratch;      /* required with params: sgr_synthesis_wgrad_scratch_bytes() bytes, 256-byte aligned */
+  size_t wgrad_scratch_bytes;
 } sgr_backward_extras;
+
+/* Gradients of the generator's own parameters (train() mode: optimize_g, libs/optimization.py:25-72),
+ * produced inside sgr_synthesis_backward_ex: the weight gradients by the tcgen05 GEMM of sgr_modconv_wgrad on the
+ * operands the backward pass already holds (demodulation term and EqualLR scale fused into its reduction pass), the
+ * per-channel ones by small reduction kernels.  Every g_* pointer is an output, fully overwritten, shaped like the
+ * reference parameter (model.py:216-224,280,348; op/fused_act.py:77); `weight` is an input.  Requires up != 1 layers. */
+typedef struct sgr_styled_param_grads {
+  const float* weight;      /* in: conv.weight[0] [cout,cin,3,3] fp32 */
+  float* g_weight;          /* [cout,cin,3,3] */
+  float* g_mod_weight;      /* [cin,512] */
+  float* g_mod_bias;        /* [cin] */
+  float* g_noise_weight;    /* [1] */
+  float* g_act_bias;        /* [cout] */
+} sgr_styled_param_grads;
+typedef struct sgr_rgb_param_grads {
+  float* g_weight;          /* [3,cin] */
+  float* g_mod_weight;      /* [cin,512] */
+  float* g_mod_bias;        /* [cin] */
+  float* g_bias;            /* [3] */
+} sgr_rgb_param_grads;
+typedef struct sgr_param_grads {
+  sgr_styled_param_grads styled[SGR_MAX_STYLED];
+  sgr_rgb_param_grads rgb[SGR_MAX_RGB];
+  float* g_const_input;     /* [cin_0,4,4] */
+} sgr_param_grads;
+size_t sgr_synthesis_wgrad_scratch_bytes(const sgr_synthesis* net, int batch);
 
 size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch);
 int sgr_synthesis_backward(const sgr_synthesis* net, const float* latent, int batch, const float* const* feats,

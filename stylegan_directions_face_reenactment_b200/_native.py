@@ -50,9 +50,22 @@ class RgbLayer(C.Structure):
                 ('bias', _fp), ('fir', _fp), ('fir_flipped', _fp)]
 
 
+class StyledParamGrads(C.Structure):
+    _fields_ = [('weight', _fp), ('g_weight', _fp), ('g_mod_weight', _fp), ('g_mod_bias', _fp), ('g_noise_weight', _fp),
+                ('g_act_bias', _fp)]
+
+
+class RgbParamGrads(C.Structure):
+    _fields_ = [('g_weight', _fp), ('g_mod_weight', _fp), ('g_mod_bias', _fp), ('g_bias', _fp)]
+
+
+class ParamGrads(C.Structure):
+    _fields_ = [('styled', StyledParamGrads * MAX_STYLED), ('rgb', RgbParamGrads * MAX_RGB), ('g_const_input', _fp)]
+
+
 class BackwardExtras(C.Structure):
     _fields_ = [('gfeats', C.POINTER(_fp)), ('ds_styled', C.POINTER(_fp)), ('ds_rgb', C.POINTER(_fp)), ('g_input', _fp),
-                ('gw_styled', C.POINTER(_fp))]
+                ('params', C.POINTER(ParamGrads)), ('wgrad_scratch', _fp), ('wgrad_scratch_bytes', C.c_size_t)]
 
 
 class WgradArgs(C.Structure):
@@ -90,6 +103,7 @@ SIGNATURES = {
     'sgr_demod': (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     'sgr_synthesis_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
     'sgr_synthesis_backward_workspace_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
+    'sgr_synthesis_wgrad_scratch_bytes': (C.c_size_t, [C.POINTER(Synthesis), C.c_int]),
     'sgr_synthesis_backward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, C.c_size_t,
                                          _fp]),
     'sgr_synthesis_backward_ex': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, C.POINTER(_fp), _fp, _fp, _fp, C.c_size_t,

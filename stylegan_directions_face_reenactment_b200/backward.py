@@ -1,11 +1,13 @@
 """dL/d(latent) through the synthesis network: one C call (sgr_synthesis_backward, csrc/backward.cu).
 
 Generator-parameter gradients (the `optimize_g` fine-tuning of libs/optimization.py:25-72) are
-assembled here from three extra outputs of the same C call — dL/d(activation) of every StyledConv, dL/d(style) of every
-layer, dL/d(modulated constant input) — with ATen operators: the weight-gradient convolutions go through
-torch.nn.grad.conv2d_weight (cuDNN), i.e. this "next" row runs on a LIBRARY wgrad, not on hand-written kernels yet.
-It is only taken in train() mode (optimize_g calls generator.train(), :29); in eval() mode (A-matrix training,
-libs/trainer.py:111,144) the generator is frozen and no weight gradient is ever formed.
+written by the same C call (sgr_backward_extras.params): the weight gradients by the tcgen05 weight-gradient GEMM
+(csrc/wgrad_sm100.cu) on the operands the backward pass already holds, the per-channel ones (modulation linears, noise
+weight, biases, ToRGB, constant input) by small reduction kernels (csrc/backward.cu).  Only a network with a layer packed
+in polyphase mode (non-separable blur kernel, never the case for the reference's [1,3,3,1]) takes the fallback below,
+which assembles the same gradients from dL/d(activation), dL/d(style) and dL/d(modulated constant input) with ATen
+operators (conv2d_weight = cuDNN).  Parameter gradients are only formed in train() mode (optimize_g calls
+generator.train(), :29); in eval() mode (A-matrix training, libs/trainer.py:111,144) the generator is frozen.
 """
 import ctypes as C
 import math
@@ -17,6 +19,7 @@ from . import _native as N
 from .synthesis import _descriptor, _workspace
 
 SQRT2 = math.sqrt(2.0)
+FORCE_ATEN_WGRAD = False      # tools/gpu_optimize_g_bench.py: time the ATen/cuDNN weight gradients against the library's
 
 
 def synthesis_param_list(g):
@@ -42,22 +45,49 @@ def synthesis_backward(g, lat, feats, noise, grad_image, want_param_grads=False)
         ws = _workspace(g, desc, batch, dev, backward=True)
         dlat = torch.empty_like(lat)
         arr = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
-        extras = None
-        if want_param_grads:
-            gfeats = [torch.empty_like(f) for f in feats]
-            ds_styled = [torch.empty(batch, l.conv.in_channel, device=dev) for l in styled]
-            ds_rgb = [torch.empty(batch, l.conv.in_channel, device=dev) for l in rgbs]
-            g_input = torch.empty(batch, styled[0].conv.in_channel, 4, 4, device=dev)
-            ex = N.BackwardExtras()
-            a1 = (C.c_void_p * len(gfeats))(*[t.data_ptr() for t in gfeats])
-            a2 = (C.c_void_p * len(ds_styled))(*[t.data_ptr() for t in ds_styled])
-            a3 = (C.c_void_p * len(ds_rgb))(*[t.data_ptr() for t in ds_rgb])
-            ex.gfeats, ex.ds_styled, ex.ds_rgb, ex.g_input = a1, a2, a3, g_input.data_ptr()
-            extras = C.byref(ex)
-        N.check(N.lib().sgr_synthesis_backward_ex(C.byref(desc.struct), N.ptr(lat), batch, arr, N.ptr(gimg), N.ptr(dlat),
-                                                  N.ptr(ws), ws.numel(), extras, N.stream()), 'sgr_synthesis_backward')
         if not want_param_grads:
+            N.check(N.lib().sgr_synthesis_backward_ex(C.byref(desc.struct), N.ptr(lat), batch, arr, N.ptr(gimg), N.ptr(dlat),
+                                                      N.ptr(ws), ws.numel(), None, N.stream()), 'sgr_synthesis_backward')
             return dlat, None
+        ex = N.BackwardExtras()
+        if all(l.conv.up_mode() in (0, 2) for l in styled) and not FORCE_ATEN_WGRAD:
+            # native path: every parameter gradient is written by the C call, straight into tensors shaped like the parameters
+            params = synthesis_param_list(g)
+            grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+            weights = [l.conv.weight.detach().contiguous().float() for l in styled]
+            pg = N.ParamGrads()
+            pg.g_const_input = grads[0].data_ptr()
+            k = 1
+            for i, l in enumerate(styled):
+                e = pg.styled[i]
+                e.weight = weights[i].data_ptr()
+                e.g_weight, e.g_mod_weight, e.g_mod_bias, e.g_noise_weight, e.g_act_bias = [t.data_ptr() for t in grads[k:k + 5]]
+                k += 5
+            for i, l in enumerate(rgbs):
+                e = pg.rgb[i]
+                e.g_weight, e.g_mod_weight, e.g_mod_bias, e.g_bias = [t.data_ptr() for t in grads[k:k + 4]]
+                k += 4
+            nscratch = N.lib().sgr_synthesis_wgrad_scratch_bytes(C.byref(desc.struct), batch)
+            wscratch = g._workspace.get((batch, dev.index, 'wgrad'))
+            if wscratch is None or wscratch.numel() < nscratch:
+                wscratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+                g._workspace[(batch, dev.index, 'wgrad')] = wscratch
+            ex.params, ex.wgrad_scratch, ex.wgrad_scratch_bytes = C.pointer(pg), wscratch.data_ptr(), nscratch
+            N.check(N.lib().sgr_synthesis_backward_ex(C.byref(desc.struct), N.ptr(lat), batch, arr, N.ptr(gimg), N.ptr(dlat),
+                                                      N.ptr(ws), ws.numel(), C.byref(ex), N.stream()), 'sgr_synthesis_backward')
+            return dlat, grads
+        # fallback (a layer packed in polyphase mode = non-separable blur kernel, or FORCE_ATEN_WGRAD): assemble the
+        # gradients from the extra outputs with ATen operators
+        gfeats = [torch.empty_like(f) for f in feats]
+        ds_styled = [torch.empty(batch, l.conv.in_channel, device=dev) for l in styled]
+        ds_rgb = [torch.empty(batch, l.conv.in_channel, device=dev) for l in rgbs]
+        g_input = torch.empty(batch, styled[0].conv.in_channel, 4, 4, device=dev)
+        a1 = (C.c_void_p * len(gfeats))(*[t.data_ptr() for t in gfeats])
+        a2 = (C.c_void_p * len(ds_styled))(*[t.data_ptr() for t in ds_styled])
+        a3 = (C.c_void_p * len(ds_rgb))(*[t.data_ptr() for t in ds_rgb])
+        ex.gfeats, ex.ds_styled, ex.ds_rgb, ex.g_input = a1, a2, a3, g_input.data_ptr()
+        N.check(N.lib().sgr_synthesis_backward_ex(C.byref(desc.struct), N.ptr(lat), batch, arr, N.ptr(gimg), N.ptr(dlat),
+                                                  N.ptr(ws), ws.numel(), C.byref(ex), N.stream()), 'sgr_synthesis_backward')
         return dlat, _param_grads(g, lat, feats, noise, gimg, gfeats, ds_styled, ds_rgb, g_input)
 
 

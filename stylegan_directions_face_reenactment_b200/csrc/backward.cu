@@ -12,6 +12,8 @@
 // No per-sample weight gradient is ever formed; generator weight gradients (optimize_g) are out of this kernel set.
 #include <string.h>
 
+#include <algorithm>
+
 #include "sgr_internal.h"
 #include "sgr_ptx.cuh"
 
@@ -310,6 +312,113 @@ __global__ void dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, 
             acc * 0.044194173824159216f);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generator-parameter gradients (train() mode, optimize_g: libs/optimization.py:25-72).
+// Per styled layer, from the saved output a and its gradient ga (gt = ga * sqrt2 * (a > 0 ? 1 : 0.2)):
+//   d(activate.bias)[o] = sum_{b,p} gt           d(noise.weight) = sum_{b,o,p} gt * noise[b?,p]
+//   d(ToRGB.conv.weight)[c,o] = sum_{b,p} grgb[b,c,p] a[b,o,p] * s_rgb[b,o] / sqrt(C)      d(ToRGB.bias)[c] = sum_{b,p} grgb
+// grid (C, B): one block per (channel, sample) walks the pixels; block reduction, then one atomic per sum.
+struct ParamSumsParams {
+  int B, C, HW;
+  const float* a;
+  long long a_bstride;
+  const float* ga;            // [B,C,HW]
+  const float* noise;         // [HW] (+ batch stride) or NULL
+  long long noise_bstride;
+  const float* grgb;          // [B,3,HW] or NULL
+  const float* s_rgb;         // [B,C]
+  float* g_act_bias;          // [C]
+  float* g_noise_w;           // [1]
+  float* g_wrgb;              // [3,C]
+  float* g_rgb_bias;          // [3]
+};
+
+__global__ void __launch_bounds__(256) param_sums_kernel(const ParamSumsParams p) {
+  __shared__ float red[8][8];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float kSqrt2 = 1.4142135623730951f;
+  const float* a = p.a + static_cast<size_t>(b) * p.a_bstride + static_cast<size_t>(c) * p.HW;
+  const float* ga = p.ga + (static_cast<size_t>(b) * p.C + c) * p.HW;
+  const float* nz = p.noise ? p.noise + static_cast<size_t>(b) * p.noise_bstride : nullptr;
+  const float* g3 = p.grgb ? p.grgb + static_cast<size_t>(b) * 3 * p.HW : nullptr;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  for (int pix = threadIdx.x; pix < p.HW; pix += blockDim.x) {
+    const float av = __ldg(a + pix);
+    const float gt = __ldg(ga + pix) * (av > 0.f ? kSqrt2 : 0.2f * kSqrt2);
+    v[0] += gt;
+    if (nz) v[1] = fmaf(gt, __ldg(nz + pix), v[1]);
+    if (g3) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float g = __ldg(g3 + static_cast<size_t>(k) * p.HW + pix);
+        v[2 + k] = fmaf(av, g, v[2 + k]);
+        v[5 + k] += g;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = warp_sum(v[k]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int k = threadIdx.x;
+    if (k == 0) atomicAdd(p.g_act_bias + c, t);
+    if (k == 1 && nz) atomicAdd(p.g_noise_w, t);
+    if (k >= 2 && k < 5 && g3)
+      atomicAdd(p.g_wrgb + (k - 2) * p.C + c, t * __ldg(p.s_rgb + static_cast<size_t>(b) * p.C + c) * rsqrtf(static_cast<float>(p.C)));
+    if (k >= 5 && g3 && c == 0) atomicAdd(p.g_rgb_bias + (k - 5), t);
+  }
+}
+
+// d(modulation.weight)[i,k] = sum_b ds[b,i] * latent[b,row,k] / sqrt(512),  d(modulation.bias)[i] = sum_b ds[b,i]
+// (EqualLinear backward, model.py:148-157) for every styled and ToRGB layer in one launch.  grid (4, cin_max, jobs).
+struct ModGradJob {
+  const float* ds;      // [B,cin]
+  float* g_weight;      // [cin,512]
+  float* g_bias;        // [cin]
+  int cin, row;
+};
+struct ModGradJobs {
+  ModGradJob job[SGR_MAX_STYLED + SGR_MAX_RGB];
+  int n;
+};
+__global__ void __launch_bounds__(128) modgrad_kernel(const ModGradJobs jobs, const float* __restrict__ latent,
+                                                      int latent_stride, int batch) {
+  const ModGradJob& j = jobs.job[blockIdx.z];
+  const int i = blockIdx.y;
+  if (i >= j.cin) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f, sum = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const float d = __ldg(j.ds + static_cast<size_t>(b) * j.cin + i);
+    sum += d;
+    acc = fmaf(d, __ldg(latent + static_cast<size_t>(b) * latent_stride + static_cast<size_t>(j.row) * SGR_STYLE_DIM + k), acc);
+  }
+  j.g_weight[static_cast<size_t>(i) * SGR_STYLE_DIM + k] = acc * 0.044194173824159216f;
+  if (k == 0) j.g_bias[i] = sum;
+}
+
+// d(ConstantInput.input)[c,p] = sum_b g_input[b,c,p] * s_0[b,c]      (model.py:290-300; the input of conv1 is input * s_0)
+__global__ void const_grad_kernel(const float* __restrict__ g_input, const float* __restrict__ s0, int batch, int C,
+                                  float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * 16) return;
+  const int c = idx / 16;
+  float acc = 0.f;
+  for (int b = 0; b < batch; ++b)
+    acc = fmaf(__ldg(g_input + static_cast<size_t>(b) * C * 16 + idx), __ldg(s0 + static_cast<size_t>(b) * C + c), acc);
+  out[idx] = acc;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct BwdPlan {
@@ -388,6 +497,33 @@ using namespace sgr;
 
 extern "C" {
 
+// caller-allocated scratch of the parameter-gradient path:
+//   [modulated layer input as a C8 operand | dL/d(layer output) fp32 | slice partials of the weight-gradient GEMM]
+static size_t wgrad_xs_bytes(const sgr_synthesis* net, int batch) {
+  size_t max_in = 0;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const size_t res_out = static_cast<size_t>(4) << ((l + 1) / 2);
+    const size_t res_in = net->styled[l].up ? res_out / 2 : res_out;
+    max_in = std::max(max_in, static_cast<size_t>(batch) * net->styled[l].cin * res_in * res_in);
+  }
+  return align_up(max_in * 4, 256);
+}
+static size_t wgrad_ga_bytes(const sgr_synthesis* net, int batch) {
+  size_t max_out = 0;
+  for (int l = 0; l < net->n_styled; ++l) {
+    const size_t res_out = static_cast<size_t>(4) << ((l + 1) / 2);
+    max_out = std::max(max_out, static_cast<size_t>(batch) * net->styled[l].cout * res_out * res_out);
+  }
+  return align_up(max_out * 4, 256);
+}
+
+size_t sgr_synthesis_wgrad_scratch_bytes(const sgr_synthesis* net, int batch) {
+  if (!net || batch <= 0 || net->n_styled < 1 || net->n_styled > SGR_MAX_STYLED) return 0;
+  size_t part = 0;
+  for (int l = 0; l < net->n_styled; ++l) part = std::max(part, wgrad_scratch_bytes(net->styled[l].cout, net->styled[l].cin));
+  return wgrad_xs_bytes(net, batch) + wgrad_ga_bytes(net, batch) + align_up(part, 256);
+}
+
 size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch) {
   BwdPlan pl;
   if (plan_backward(net, batch, &pl)) return 0;
@@ -426,6 +562,43 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   const int latent_stride = net->n_latent * SGR_STYLE_DIM;
   const int L = net->n_styled, R = net->n_rgb;
+  const sgr_param_grads* pg = extras ? extras->params : nullptr;
+  const size_t xs_bytes = wgrad_xs_bytes(net, batch), ga_bytes = wgrad_ga_bytes(net, batch);
+  if (pg) {
+    if (!extras->wgrad_scratch || (reinterpret_cast<uintptr_t>(extras->wgrad_scratch) & 255) != 0 ||
+        extras->wgrad_scratch_bytes < sgr_synthesis_wgrad_scratch_bytes(net, batch)) {
+      set_error("synthesis_backward: parameter gradients need %zu bytes of 256-byte aligned wgrad_scratch",
+                sgr_synthesis_wgrad_scratch_bytes(net, batch));
+      return 1;
+    }
+    bool ok = pg->g_const_input != nullptr;
+    for (int l = 0; l < net->n_styled && ok; ++l) {
+      const sgr_styled_param_grads& g = pg->styled[l];
+      ok = g.weight && g.g_weight && g.g_mod_weight && g.g_mod_bias && g.g_noise_weight && g.g_act_bias &&
+           net->styled[l].up != 1;
+    }
+    for (int r = 0; r < net->n_rgb && ok; ++r) {
+      const sgr_rgb_param_grads& g = pg->rgb[r];
+      ok = g.g_weight && g.g_mod_weight && g.g_mod_bias && g.g_bias;
+    }
+    if (!ok) {
+      set_error("synthesis_backward: sgr_param_grads has a null pointer, or a layer is packed in polyphase mode (up == 1)");
+      return 1;
+    }
+    for (int l = 0; l < net->n_styled; ++l)
+      if (cudaMemsetAsync(pg->styled[l].g_noise_weight, 0, 4, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
+          cudaMemsetAsync(pg->styled[l].g_act_bias, 0, static_cast<size_t>(net->styled[l].cout) * 4,
+                          static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+        set_error("synthesis_backward: memset failed");
+        return 1;
+      }
+    for (int r = 0; r < net->n_rgb; ++r)
+      if (cudaMemsetAsync(pg->rgb[r].g_weight, 0, static_cast<size_t>(net->rgb[r].cin) * 12, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
+          cudaMemsetAsync(pg->rgb[r].g_bias, 0, 12, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+        set_error("synthesis_backward: memset failed");
+        return 1;
+      }
+  }
 
   // styles + demod (recomputed: cheaper than keeping them alive between forward and backward)
   StyleJobs sj;
@@ -500,6 +673,7 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
     p.noise_bstride = Ly.noise_batch_stride;
     p.noise_w = Ly.noise_weight;
     if (extras && extras->gfeats) p.out_ga = extras->gfeats[l];
+    if (pg && !p.out_ga) p.out_ga = reinterpret_cast<float*>(static_cast<char*>(extras->wgrad_scratch) + xs_bytes);
     const bool scatter = Ly.up == 2;      // gather adjoint: FIR^T to parity planes, then the 9 real taps
     if (scatter) p.out_gz4 = F(pl.gz_off);
     else p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
@@ -528,6 +702,43 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
       count_launch();
       if (!check_launch("up_bwd_prepare_kernel")) return 1;
     }
+    // generator-parameter gradients (optimize_g): per-channel sums, then the weight-gradient GEMM of the gz operand just
+    // built x the modulated layer input, re-split from the saved fp32 activation of the previous layer (conv1: the constant)
+    if (pg) {
+      ParamSumsParams sp;
+      memset(&sp, 0, sizeof(sp));
+      sp.B = batch; sp.C = Ly.cout; sp.HW = res_out * res_out;
+      sp.a = feats[l]; sp.a_bstride = p.a_bstride; sp.ga = p.out_ga;
+      sp.noise = Ly.noise; sp.noise_bstride = Ly.noise_batch_stride;
+      if (!Ly.up) {
+        sp.grgb = grgb[r]; sp.s_rgb = F(pl.rgbstyle_off[r]);
+        sp.g_wrgb = pg->rgb[r].g_weight; sp.g_rgb_bias = pg->rgb[r].g_bias;
+      }
+      sp.g_act_bias = pg->styled[l].g_act_bias; sp.g_noise_w = pg->styled[l].g_noise_weight;
+      param_sums_kernel<<<dim3(Ly.cout, batch), 256, 0, st>>>(sp);
+      count_launch();
+      if (!check_launch("param_sums_kernel")) return 1;
+
+      char* xs = static_cast<char*>(extras->wgrad_scratch);
+      if (l == 0) {
+        if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, Ly.cin, SGR_FMT_BF16, xs, st)) return 1;
+      } else if (nchw_to_c8_launch(feats[l - 1], F(pl.style_off[l]), xs, batch, Ly.cin, res_in, res_in, 0, SGR_FMT_BF16, st)) {
+        return 1;
+      }
+      sgr_wgrad_args wa;
+      memset(&wa, 0, sizeof(wa));
+      wa.batch = batch; wa.cin = Ly.cin; wa.cout = Ly.cout; wa.h_in = res_in; wa.w_in = res_in;
+      wa.up = scatter ? 2 : 0;
+      wa.x_c8 = xs;
+      wa.gz_c8 = scatter ? ws + pl.planes_off : ws + pl.gz_off;
+      wa.gw = pg->styled[l].g_weight;
+      wa.scratch = xs + xs_bytes + ga_bytes;
+      wa.scratch_bytes = extras->wgrad_scratch_bytes - xs_bytes - ga_bytes;
+      WgradFinish wf;
+      wf.weight = pg->styled[l].weight; wf.q = F(pl.q_off[l]); wf.demod = F(pl.demod_off[l]); wf.style = F(pl.style_off[l]);
+      wf.batch = batch; wf.scale = 1.f / sqrtf(static_cast<float>(Ly.cin) * 9.f);
+      if (wgrad_launch(&wa, &wf, st)) return 1;
+    }
     a.cin = scatter ? Ly.cout : (Ly.up ? 4 * Ly.cout : Ly.cout);
     a.cout = Ly.cin;
     a.h_in = res_in;
@@ -553,6 +764,12 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
                       st) != cudaSuccess) {
     set_error("synthesis_backward: copy of g_input failed");
     return 1;
+  }
+  if (pg && gx_next) {
+    const int C0 = net->styled[0].cin;
+    const_grad_kernel<<<(C0 * 16 + 127) / 128, 128, 0, st>>>(gx_next, F(pl.style_off[0]), batch, C0, pg->g_const_input);
+    count_launch();
+    if (!check_launch("const_grad_kernel")) return 1;
   }
   // conv term of ds_0: the input of conv1 is the constant 4x4 tensor (batch stride 0)
   {
@@ -599,6 +816,24 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
         set_error("synthesis_backward: copy of ds_rgb failed");
         return 1;
       }
+  }
+  if (pg) {
+    ModGradJobs mj;
+    mj.n = 0;
+    int cmax = 0;
+    for (int l = 0; l < L; ++l) {
+      mj.job[mj.n++] = ModGradJob{F(pl.ds_off[l]), pg->styled[l].g_mod_weight, pg->styled[l].g_mod_bias, net->styled[l].cin,
+                                  net->styled[l].latent_row};
+      cmax = std::max(cmax, net->styled[l].cin);
+    }
+    for (int r = 0; r < R; ++r) {
+      mj.job[mj.n++] = ModGradJob{F(pl.dsrgb_off[r]), pg->rgb[r].g_mod_weight, pg->rgb[r].g_mod_bias, net->rgb[r].cin,
+                                  net->rgb[r].latent_row};
+      cmax = std::max(cmax, net->rgb[r].cin);
+    }
+    modgrad_kernel<<<dim3(SGR_STYLE_DIM / 128, cmax, mj.n), 128, 0, st>>>(mj, latent, latent_stride, batch);
+    count_launch();
+    if (!check_launch("modgrad_kernel")) return 1;
   }
   LatJobs lj;
   lj.n = 0;

@@ -99,7 +99,15 @@ int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t
 
 // wgrad_sm100.cu: weight-gradient GEMM (K = pixels, MN-major operands)
 size_t wgrad_scratch_bytes(int cout, int cin);
-int wgrad_launch(const sgr_wgrad_args* a, cudaStream_t stream);
+struct WgradFinish {      // optional fused tail: demodulation term + the EqualLR scale -> gradient of conv.weight itself
+  const float* weight;    // [cout,cin,3,3] fp32 parameter (NULL: raw convolution term)
+  const float* q;         // [B,cout]
+  const float* demod;     // [B,cout]
+  const float* style;     // [B,cin]
+  int batch;
+  float scale;            // 1/sqrt(cin*9)
+};
+int wgrad_launch(const sgr_wgrad_args* a, const WgradFinish* finish, cudaStream_t stream);
 
 // prep_kernels.cu
 struct StyleJob {

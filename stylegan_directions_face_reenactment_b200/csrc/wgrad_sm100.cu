@@ -208,9 +208,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
   }
 }
 
-// gw[o][i][tap] = sum_s part[s][tap][o][i], slices in order
+// gw[o][i][tap] = sum_s part[s][tap][o][i], slices in order.  With `f` (the synthesis backward pass) the result is the
+// finished gradient of the reference parameter conv.weight (model.py:216-218), demodulation term included:
+//   dW[o,i,k] = scale * ( gw[o,i,k] - scale * W[o,i,k] * sum_b q[b,o] d[b,o]^2 s[b,i]^2 )
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ part, int slices, int cout, int cin,
-                                                           float* __restrict__ gw) {
+                                                           float* __restrict__ gw, const WgradFinish f) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= cout * cin) return;
   const size_t tap_stride = static_cast<size_t>(cout) * cin;
@@ -221,6 +223,17 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
     const float* src = part + static_cast<size_t>(s) * 9 * tap_stride + idx;
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] += __ldcs(src + t * tap_stride);
+  }
+  if (f.weight) {
+    const int o = idx / cin, i = idx - o * cin;
+    float dterm = 0.f;
+    for (int b = 0; b < f.batch; ++b) {
+      const float d = __ldg(f.demod + static_cast<size_t>(b) * cout + o), sv = __ldg(f.style + static_cast<size_t>(b) * cin + i);
+      dterm = fmaf(__ldg(f.q + static_cast<size_t>(b) * cout + o) * d * d, sv * sv, dterm);
+    }
+    dterm *= f.scale;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = f.scale * fmaf(-dterm, __ldg(f.weight + static_cast<size_t>(idx) * 9 + t), acc[t]);
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t) gw[static_cast<size_t>(idx) * 9 + t] = acc[t];
@@ -245,7 +258,7 @@ size_t wgrad_scratch_bytes(int cout, int cin) {
   return per_slice * s;
 }
 
-int wgrad_launch(const sgr_wgrad_args* a, cudaStream_t stream) {
+int wgrad_launch(const sgr_wgrad_args* a, const WgradFinish* finish, cudaStream_t stream) {
   const int sms = num_sms();
   if (sms <= 0) {
     set_error("modconv_wgrad: no CUDA device");
@@ -335,7 +348,10 @@ int wgrad_launch(const sgr_wgrad_args* a, cudaStream_t stream) {
   wgrad_kernel<<<std::min(total_items, sms), 256, smem_bytes, stream>>>(tmap_a, tmap_b, p);
   count_launch();
   if (!check_launch("wgrad_kernel")) return 1;
-  wgrad_finish_kernel<<<(a->cout * a->cin + 255) / 256, 256, 0, stream>>>(p.part, p.slices, a->cout, a->cin, a->gw);
+  WgradFinish f;
+  memset(&f, 0, sizeof(f));
+  if (finish) f = *finish;
+  wgrad_finish_kernel<<<(a->cout * a->cin + 255) / 256, 256, 0, stream>>>(p.part, p.slices, a->cout, a->cin, a->gw, f);
   count_launch();
   return check_launch("wgrad_finish_kernel") ? 0 : 1;
 }
@@ -359,7 +375,7 @@ int sgr_modconv_wgrad(const sgr_wgrad_args* args, void* stream) {
     set_error("modconv_wgrad: null arguments");
     return 1;
   }
-  return wgrad_launch(args, static_cast<cudaStream_t>(stream));
+  return wgrad_launch(args, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -467,6 +467,53 @@ def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates(pkg):
     assert wg.grad is not None and torch.isfinite(wg.grad).all()
 
 
+@pytest.mark.parametrize('b,cin,cout,h,up', [(2, 64, 64, 8, 0), (1, 128, 128, 16, 0), (1, 128, 128, 16, 1), (3, 512, 512, 4, 0),
+                                             (1, 256, 128, 32, 1), (2, 32, 32, 4, 0), (1, 64, 64, 20, 0), (1, 64, 32, 12, 1),
+                                             (2, 64, 64, 64, 0)])
+def test_modconv_wgrad_vs_aten_fp64(pkg, b, cin, cout, h, up):
+    """sgr_modconv_wgrad (tcgen05 GEMM over pixels, csrc/wgrad_sm100.cu) against the weight gradient the reference gets from
+    ATen autograd of F.conv2d / F.conv_transpose2d (model.py:254,269), evaluated in fp64 on the CPU.  bf16 hi/lo operands,
+    3 MMAs per product: 5e-5 of the tensor's max (measured 4e-6 .. 2e-5); twice in a row bit-identical (slice order fixed)."""
+    import ctypes as C
+    from stylegan_directions_face_reenactment_b200 import _native as N
+    rng = np.random.Generator(np.random.PCG64(b * 1000 + cin + cout + h + up))
+    x = T(rng.standard_normal((b, cin, h, h), dtype=np.float32))
+    g = T(rng.standard_normal((b, cout, 2 * h + 1, 2 * h + 1) if up else (b, cout, h, h), dtype=np.float32))
+    if up:
+        ref = torch.nn.grad.conv2d_weight(g.double(), (cin, cout, 3, 3), x.double(), stride=2).transpose(0, 1)
+        gp = torch.zeros(b, cout, 2 * h + 2, 2 * h + 2)
+        gp[:, :, :2 * h + 1, :2 * h + 1] = g
+        gop = torch.cat([gp[:, :, pu::2, pv::2] for pu in (0, 1) for pv in (0, 1)], 1).contiguous()   # parity planes as channels
+    else:
+        ref = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, 3, 3), g.double(), padding=1)
+        gop = g
+    lib = N.lib()
+
+    def c8(t):
+        t = t.cuda().contiguous()
+        o = torch.empty(2 * t.numel(), dtype=torch.bfloat16, device='cuda')
+        N.check(lib.sgr_nchw_to_c8(N.ptr(t), None, N.ptr(o), t.shape[0], t.shape[1], t.shape[2], t.shape[3], 0, N.FMT_BF16,
+                                   N.stream()), 'sgr_nchw_to_c8')
+        return o
+    xc8, gc8 = c8(x), c8(gop)
+    nbytes = lib.sgr_wgrad_scratch_bytes(cout, cin)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    outs = []
+    for _ in range(2):
+        gw = torch.full((cout, cin, 3, 3), float('nan'), device='cuda')
+        a = N.WgradArgs()
+        a.batch, a.cin, a.cout, a.h_in, a.w_in, a.up = b, cin, cout, h, h, 2 if up else 0
+        a.x_c8, a.gz_c8, a.gw, a.scratch, a.scratch_bytes = N.ptr(xc8), N.ptr(gc8), N.ptr(gw), N.ptr(scratch), nbytes
+        N.check(lib.sgr_modconv_wgrad(C.byref(a), N.stream()), 'sgr_modconv_wgrad')
+        outs.append(gw.cpu())
+    assert torch.equal(outs[0], outs[1])
+    scale = float(ref.abs().max())
+    assert float((outs[0].double() - ref).abs().max()) <= 5e-5 * scale
+    # too little scratch is an error, not a silent fallback
+    a.scratch_bytes = 9 * cout * cin * 4 - 1
+    assert lib.sgr_modconv_wgrad(C.byref(a), N.stream()) != 0
+
+
 @pytest.mark.parametrize('size,cm,batch', [(8, 2, 2), (32, 2, 2)])
 def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
     """SURVEY 8f-1 (optimize_g, libs/optimization.py:25-72): in train() mode every parameter the synthesis path reads gets
@@ -501,6 +548,19 @@ def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
             assert cos >= 0.999, (name, cos)
         checked += 1
     assert checked == 1 + 5 * G.num_layers + 4 * (G.log_size - 1)
+    # the ATen fallback (taken for polyphase-packed layers) assembles the same gradients from the extra outputs
+    from stylegan_directions_face_reenactment_b200 import backward as bwd
+    native = {n: p.grad.clone() for n, p in G.named_parameters() if p.grad is not None}
+    G.zero_grad(set_to_none=True)
+    bwd.FORCE_ATEN_WGRAD = True
+    try:
+        (G([wplus.cuda()], input_is_latent=True)[0] * r.cuda()).sum().backward()
+    finally:
+        bwd.FORCE_ATEN_WGRAD = False
+    for n, p in G.named_parameters():
+        if n in native:
+            scale = float(native[n].abs().max())
+            assert float((p.grad - native[n]).abs().max()) <= 5e-3 * max(scale, 1e-6), n      # cuDNN wgrad runs in TF32
     # eval() mode: the generator is frozen (A-matrix training): no parameter gradient is formed
     G.zero_grad(set_to_none=True)
     G.eval()
