@@ -110,10 +110,13 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
         const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
-          mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
-          mbar_expect_tx(&a_full[as], a_bytes);
-          tma_load_5d(a_base + as * Cfg::kABytes, &tmap, &a_full[as], x0 * 8, y0, b, kb * 4, 0);
+          if (!(p.debug & 16) || ai < AS) {     // experiment 16: A ring loaded once
+            mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
+            mbar_expect_tx(&a_full[as], a_bytes);
+            tma_load_5d(a_base + as * Cfg::kABytes, &tmap, &a_full[as], x0 * 8, y0, b, kb * 4, 0);
+          }
           for (int tap = 0; tap < 9; ++tap, ++bi) {
+            if ((p.debug & 4) && bi >= BS) continue;   // experiment 4: weight ring loaded once
             const uint32_t bs = bi % BS;
             mbar_wait(&b_empty[bs], ((bi / BS) & 1) ^ 1);
             mbar_expect_tx(&b_full[bs], b_bytes);
@@ -141,16 +144,41 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
         const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
-          mbar_wait(&a_full[as], (ai / AS) & 1);
+          if (!(p.debug & 16) || ai < AS) mbar_wait(&a_full[as], (ai / AS) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_base + as * Cfg::kABytes);
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bi) {
             const uint32_t bs = bi % BS;
-            mbar_wait(&b_full[bs], (bi / BS) & 1);
+            if (!(p.debug & 4) || bi < BS) mbar_wait(&b_full[bs], (bi / BS) & 1);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(b_base + bs * Cfg::kBBytes);
             const uint32_t tap_off = static_cast<uint32_t>((tap / 3) * Cfg::kHW + (tap % 3)) * 16;
+            if (Cfg::kConcat && !p.single && !(p.debug & 32)) {
+              // MMAs of one shape are issued together: alternating the N = 2 NT and N = NT instructions on the same
+              // accumulator columns costs ~25 ns per switch (measured: 0.64 -> 0.52 ms on the 64 -> 64 layer at 256^2 with
+              // the pairs two MMAs apart, debug 32 = the old alternating order)
+#pragma unroll
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t a_off = a_addr + tap_off + mt * 128 + j * 2 * kALbo;
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, umma_desc(a_off, kALbo, kASbo), b_hi, idesc_cat,
+                            (kb > kb0 || (tap | j) != 0));                                   // hi*hi | hi*lo
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint32_t a_off = a_addr + tap_off + mt * 128 + j * 2 * kALbo;
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, umma_desc(a_off + kAPlane, kALbo, kASbo), b_hi,
+                            (p.debug & 64) ? idesc_cat : idesc, 1);                           // lo*hi
+                }
+              }
+            } else {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -163,7 +191,7 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
                   umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc, (kb > kb0 || (tap | j) != 0));
                 } else if (Cfg::kConcat) {
                   umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, (kb > kb0 || (tap | j) != 0));   // hi*hi | hi*lo
-                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, idesc, 1);                         // lo*hi
+                  umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, (p.debug & 64) ? idesc_cat : idesc, 1);   // lo*hi (64: + lo*lo)
                 } else {
                   const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
                   umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, (kb > kb0 || (tap | j) != 0));
@@ -171,6 +199,7 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
                   umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
                 }
               }
+            }
             }
             umma_commit(&b_empty[bs]);     // weight slab consumed
           }
@@ -200,7 +229,7 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = 0; mt < ((p.debug & 8) ? 0 : MT); ++mt) {      // experiment 8: no epilogue work
         const int x = tx * Cfg::kTileW + mt * 8 + (r & 7);
         const bool valid = y < p.H && x < p.W;
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
