@@ -226,10 +226,33 @@ def golden_output_stage():
     save('output_stage.npz', x=x, y=y, y_pooled=yp)
 
 
+def golden_formats():
+    """Files written the way the reference writes them: an A-matrix checkpoint with the dict of
+    libs/utilities/utils_train.py:592-603 around the reference DirectionMatrix's state_dict, and one inverted-code .npy as
+    invert_images.py:118-125 saves it (latent_codes[i].detach().cpu().numpy() -> np.save)."""
+    torch.manual_seed(21)
+    A = RefDirectionMatrix(shift_dim=512, input_dim=15, out_dim=None, w_plus=True, bias=True, num_layers=8)
+    with torch.no_grad():
+        A.linear.bias.normal_(0, 0.01)
+    state_dict = {'step': 10, 'A_matrix': A.state_dict(), 'learned_directions': 15, 'shift_scale': 6, 'w_plus': True,
+                  'num_layers_shift': 8}
+    torch.save(state_dict, os.path.join(ROOT, 'tests', 'golden', 'A_matrix_000010.pt'))
+    dp = rnd(np.random.Generator(np.random.PCG64(22)), 3, 15)
+    shift = A(dp).detach().numpy()
+    G, _ = _ref_generator(8, 2, 3)
+    latent_codes = G.style(rnd(np.random.Generator(np.random.PCG64(23)), 1, 512)).unsqueeze(1).repeat(1, G.n_latent, 1)
+    latent_code = latent_codes[0].detach().cpu().numpy()
+    np.save(os.path.join(ROOT, 'tests', 'golden', 'latent_000.npy'), latent_code)
+    save('formats.npz', dp=dp.numpy(), shift=shift, latent=latent_code)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'output_stage':
         golden_output_stage()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'formats':
+        golden_formats()
         sys.exit(0)
     golden_upfirdn2d()
     golden_bias_act()
@@ -238,3 +261,4 @@ if __name__ == '__main__':
     golden_generator()
     golden_reenact()
     golden_output_stage()
+    golden_formats()

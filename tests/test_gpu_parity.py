@@ -235,6 +235,33 @@ def test_reenact_forward_golden(pkg, golden):
     assert err(img, g['img']) <= 1e-3
 
 
+def test_reenact_from_files(pkg, golden, tmp_path):
+    """the same reenactment as test_reenact_forward_golden with every input read from disk in the reference's
+    formats (generator checkpoint 'g_ema', A_matrix_*.pt dict, per-frame [n_latent,512] .npy) through formats.py; the
+    loader warms the packed weights (forward and adjoint) at load time."""
+    import os
+    from stylegan_directions_face_reenactment_b200 import formats
+    g = golden('reenact_32.npz')
+    size, cm, seed, batch = [int(v) for v in g['cfg']]
+    torch.save({'g_ema': orc.seeded_state_dict(size, cm, seed=seed)}, str(tmp_path / 'stylegan2.pt'))
+    torch.save({'step': 7, 'A_matrix': {'linear.weight': T(g['A_w']), 'linear.bias': T(g['A_b'])}, 'learned_directions': 15,
+                'shift_scale': 6, 'w_plus': True, 'num_layers_shift': 4}, str(tmp_path / 'A_matrix_000007.pt'))
+    os.mkdir(str(tmp_path / 'latent_codes'))
+    for i in range(batch):
+        formats.save_latent_code(str(tmp_path / 'latent_codes' / ('%06d.npy' % i)), g['wsrc'][i])
+    G = formats.load_generator(str(tmp_path / 'stylegan2.pt'), size, channel_multiplier=cm, strict=True, warm_batch=batch,
+                               backward=True)
+    assert all(l.conv._pack_cache for l in G.styled_layers())           # packed at load time
+    A, meta = formats.load_direction_matrix(str(tmp_path / 'A_matrix_000007.pt'))
+    assert meta['num_layers_shift'] == 4 and meta['shift_dim'] == 512
+    codes = formats.load_latent_codes(str(tmp_path / 'latent_codes'), n_latent=G.n_latent)
+    assert codes.is_pinned()
+    with torch.no_grad():
+        img = pkg.generate_image(G, codes.cuda(non_blocking=True), 0.7, cuda(g['trunc']), w_plus=meta['w_plus'],
+                                 num_layers_shift=meta['num_layers_shift'], shift_code=A(cuda(g['dp'])), input_is_latent=True)
+    assert err(img, g['img']) <= 1e-3
+
+
 def test_weight_cache_invalidation(pkg):
     size, cm = 8, 2
     sd = orc.seeded_state_dict(size, cm, seed=8)
