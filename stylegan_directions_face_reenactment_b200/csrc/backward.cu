@@ -318,7 +318,7 @@ __global__ void dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, 
 // Per styled layer, from the saved output a and its gradient ga (gt = ga * sqrt2 * (a > 0 ? 1 : 0.2)):
 //   d(activate.bias)[o] = sum_{b,p} gt           d(noise.weight) = sum_{b,o,p} gt * noise[b?,p]
 //   d(ToRGB.conv.weight)[c,o] = sum_{b,p} grgb[b,c,p] a[b,o,p] * s_rgb[b,o] / sqrt(C)      d(ToRGB.bias)[c] = sum_{b,p} grgb
-// grid (C, B): one block per (channel, sample) walks the pixels; block reduction, then one atomic per sum.
+// grid (C, B, pixel spans): a block walks its span of one (channel, sample) plane; block reduction, one atomic per sum.
 struct ParamSumsParams {
   int B, C, HW;
   const float* a;
@@ -345,7 +345,9 @@ __global__ void __launch_bounds__(256) param_sums_kernel(const ParamSumsParams p
   float v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] = 0.f;
-  for (int pix = threadIdx.x; pix < p.HW; pix += blockDim.x) {
+  const int span = (p.HW + gridDim.z - 1) / gridDim.z;
+  const int pix_end = min(p.HW, static_cast<int>(blockIdx.z + 1) * span);
+  for (int pix = blockIdx.z * span + threadIdx.x; pix < pix_end; pix += blockDim.x) {
     const float av = __ldg(a + pix);
     const float gt = __ldg(ga + pix) * (av > 0.f ? kSqrt2 : 0.2f * kSqrt2);
     v[0] += gt;
@@ -715,7 +717,8 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
         sp.g_wrgb = pg->rgb[r].g_weight; sp.g_rgb_bias = pg->rgb[r].g_bias;
       }
       sp.g_act_bias = pg->styled[l].g_act_bias; sp.g_noise_w = pg->styled[l].g_noise_weight;
-      param_sums_kernel<<<dim3(Ly.cout, batch), 256, 0, st>>>(sp);
+      const int spans = std::max(1, std::min(32, sp.HW / 2048));      // >= 2048 pixels per block, enough blocks at batch 1
+      param_sums_kernel<<<dim3(Ly.cout, batch, spans), 256, 0, st>>>(sp);
       count_launch();
       if (!check_launch("param_sums_kernel")) return 1;
 

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------- host side
 static int wgrad_slices(int sms, int base_items, int n_ptiles, int cout, int cin, size_t scratch_bytes) {
-  int s = (2 * sms + base_items - 1) / base_items;
+  int s = (sms + base_items - 1) / base_items;       // one wave of work items: the finish pass reads every slice
   s = std::max(1, std::min(std::min(s, 128), n_ptiles));
   const size_t per_slice = static_cast<size_t>(9) * cout * cin * 4;
   const size_t cap = scratch_bytes / per_slice;

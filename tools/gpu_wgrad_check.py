@@ -1,5 +1,5 @@
 """GPU check of sgr_modconv_wgrad (csrc/wgrad_sm100.cu) against ATen in fp64, per tap, with timing.
-   python tools/gpu_wgrad_check.py [quick]"""
+   python tools/gpu_wgrad_check.py [quick | big | ncu]"""
 import ctypes as C
 import os
 import sys
@@ -100,6 +100,10 @@ def case(b, cin, cout, h, up, timing=True):
 
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == 'quick'
+    if len(sys.argv) > 1 and sys.argv[1] in ('big', 'ncu'):     # ncu: one launch per case (profiler capture)
+        for c in [(8, 512, 512, 32, 0), (8, 256, 256, 64, 0), (8, 64, 64, 256, 0), (8, 128, 64, 128, 1), (32, 512, 512, 32, 0)]:
+            case(*c, timing=sys.argv[1] == 'big')
+        return
     cases = [(1, 128, 128, 16, 0), (1, 128, 128, 16, 1), (2, 64, 64, 8, 0), (2, 32, 32, 4, 0), (1, 256, 128, 32, 1),
              (3, 512, 512, 4, 0), (2, 512, 512, 8, 1)]
     if not quick:

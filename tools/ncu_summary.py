@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 
-def launches(src, dst, cmd_note=''):
+def launches(src, dst, cmd_note='', what='python bench.py --steps 2 --warmup 3 --cpu-baseline 0'):
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
     hdr = rows[0]
     ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
@@ -26,10 +26,10 @@ def launches(src, dst, cmd_note=''):
         agg[name] = (n + 1, tot + t)
     total = sum(t for _, t in agg.values())
     with open(dst, 'w') as f:
-        f.write('# ncu launch list of `python bench.py --steps 2 --warmup 3 --cpu-baseline 0`\n\n')
-        f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file '
-                'gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --cpu-baseline 0` (B200; cold-cache, '
-                'serialised launches: compare shares, not absolutes). %s\n\n' % cmd_note)
+        f.write('# ncu launch list of `%s`\n\n' % what)
+        f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c <N> --csv --log-file '
+                'gpurun_out/launches.csv %s` (B200; cold-cache, '
+                'serialised launches: compare shares, not absolutes). %s\n\n' % (what, cmd_note))
         f.write('| kernel | launches | total us | share |\n|---|---|---|---|\n')
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %d | %.1f | %.1f%% |\n' % (name[:90], n, t, 100 * t / total))
@@ -79,6 +79,6 @@ def full(src, dst_md, dst_json):
 
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
-        launches(sys.argv[2], sys.argv[3])
+        launches(sys.argv[2], sys.argv[3], *([''] + sys.argv[4:5] if len(sys.argv) > 4 else []))
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4])
