@@ -293,6 +293,29 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps, finish_e2e)
     e2e_value = frames / (ms_e2e * 1e-3)
+
+    # ---- same, delivering the frames the way run_inference.py consumes them (uint8 HWC): the fused output
+    # stage runs on the device and a quarter of the bytes cross PCIe.  Reported next to the fp32 number, not instead of it.
+    u8_host = [torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def step_e2e_u8(i):
+        with torch.no_grad():
+            dp = dp_host[i % len(dp_host)].to(device, non_blocking=True)
+            img = pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
+                                     input_is_latent=True)
+            u8 = pkg.frames_to_uint8(img)
+        ready = torch.cuda.Event()
+        ready.record()
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            u8_host[slot].copy_(u8, non_blocking=True)
+            u8.record_stream(copy_stream)
+            done[slot].record(copy_stream)
+
+    for i in range(3):
+        step_e2e_u8(i)
+    ms_e2e_u8 = timed(step_e2e_u8, args.steps, finish_e2e)
     clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed regions
 
     # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch)
@@ -360,7 +383,10 @@ def main():
                            'l2': 'inputs larger than L2: ~2 GB of activations stream per step',
                            'parallelism': 'frames sharded over %d rank(s), no collective' % world},
                 'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': BATCH * 15 * 4,
-                        'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE * 4, 'ms_per_step': ms_e2e / args.steps},
+                        'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE * 4, 'ms_per_step': ms_e2e / args.steps,
+                        'uint8_frames': {'value': frames / (ms_e2e_u8 * 1e-3), 'unit': 'frames/s',
+                                         'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE,
+                                         'note': 'same loop with the fused uint8 HWC output stage (sgr_frames_to_uint8)'}},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
                 'layers': layers}
         print(json.dumps(line), flush=True)

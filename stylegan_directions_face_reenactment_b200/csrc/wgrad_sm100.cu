@@ -40,6 +40,8 @@ struct WgradGroup {
   int ntaps;           // <= 4
   int tap_off[4];      // byte offset of the tap's first pixel inside the gz box
   int tap_out[4];      // ky * 3 + kx
+  int slices;          // pixel slices of this group (proportional to ntaps: every work item does the same number of MMAs)
+  int item_base;       // first work item of this group
 };
 
 struct WgradParams {
@@ -47,11 +49,12 @@ struct WgradParams {
   int bw, bh;                    // xs tile
   int tiles_x, tiles_y, n_ptiles;
   int o_tiles, i_tiles, nt, cout, cin;
-  int n_groups, slices, stages;
+  int n_groups, total_items, stages;
+  int tap_base[9], tap_slices[9]; // partial slots of output tap t: part[tap_base[t] + s], s < tap_slices[t]
   uint32_t a_bytes, b_bytes;     // gz box / xs box, both planes
   uint32_t a_sbo, a_lbo, a_kstep;
   WgradGroup g[4];
-  float* part;                   // [slices][9][cout][cin]
+  float* part;                   // [tap slot][cout][cin]
 };
 
 struct WgItem {
@@ -59,12 +62,17 @@ struct WgItem {
 };
 __device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
   WgItem w;
-  w.s = item % p.slices; item /= p.slices;
-  w.it = item % p.i_tiles; item /= p.i_tiles;
-  w.ot = item % p.o_tiles;
-  w.g = item / p.o_tiles;
-  w.p0 = static_cast<int>(static_cast<long long>(w.s) * p.n_ptiles / p.slices);
-  w.p1 = static_cast<int>(static_cast<long long>(w.s + 1) * p.n_ptiles / p.slices);
+  w.g = 0;
+#pragma unroll
+  for (int g = 1; g < 4; ++g)
+    if (g < p.n_groups && item >= p.g[g].item_base) w.g = g;
+  const int slices = p.g[w.g].slices;
+  item -= p.g[w.g].item_base;
+  w.s = item % slices; item /= slices;
+  w.it = item % p.i_tiles;
+  w.ot = item / p.i_tiles;
+  w.p0 = static_cast<int>(static_cast<long long>(w.s) * p.n_ptiles / slices);
+  w.p1 = static_cast<int>(static_cast<long long>(w.s + 1) * p.n_ptiles / slices);
   return w;
 }
 
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_items = p.n_groups * p.o_tiles * p.i_tiles * p.slices;
+  const int total_items = p.total_items;
   const int tiles_per_image = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
       mbar_wait(tfull, icount & 1);
       tc_fence_after();
       for (int t = 0; t < G.ntaps; ++t) {
-        float* dst = p.part + ((static_cast<size_t>(w.s) * 9 + G.tap_out[t]) * p.cout + o) * p.cin + w.it * p.nt;
+        float* dst = p.part + (static_cast<size_t>(p.tap_base[G.tap_out[t]] + w.s) * p.cout + o) * p.cin + w.it * p.nt;
 #pragma unroll 1
         for (int c = 0; c < p.nt; c += 32) {
           float v[32];
@@ -208,21 +216,31 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
   }
 }
 
-// gw[o][i][tap] = sum_s part[s][tap][o][i], slices in order.  With `f` (the synthesis backward pass) the result is the
+struct WgradSlots {
+  int base[9], count[9];
+};
+
+// gw[o][i][tap] = sum_s part[slot(tap) + s][o][i], slices in order.  With `f` (the synthesis backward pass) the result is the
 // finished gradient of the reference parameter conv.weight (model.py:216-218), demodulation term included:
 //   dW[o,i,k] = scale * ( gw[o,i,k] - scale * W[o,i,k] * sum_b q[b,o] d[b,o]^2 s[b,i]^2 )
-__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ part, int slices, int cout, int cin,
-                                                           float* __restrict__ gw, const WgradFinish f) {
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ part, const WgradSlots slots, int cout,
+                                                           int cin, float* __restrict__ gw, const WgradFinish f) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= cout * cin) return;
   const size_t tap_stride = static_cast<size_t>(cout) * cin;
   float acc[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-  for (int s = 0; s < slices; ++s) {
-    const float* src = part + static_cast<size_t>(s) * 9 * tap_stride + idx;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] += __ldcs(src + t * tap_stride);
+  for (int t = 0; t < 9; ++t) {
+    const float* src = part + static_cast<size_t>(slots.base[t]) * tap_stride + idx;
+    float a = 0.f;
+    int s = 0;
+    for (; s + 4 <= slots.count[t]; s += 4) {            // four loads in flight, added in slice order
+      const float v0 = __ldcs(src + (s + 0) * tap_stride), v1 = __ldcs(src + (s + 1) * tap_stride);
+      const float v2 = __ldcs(src + (s + 2) * tap_stride), v3 = __ldcs(src + (s + 3) * tap_stride);
+      a = (((a + v0) + v1) + v2) + v3;
+    }
+    for (; s < slots.count[t]; ++s) a += __ldcs(src + s * tap_stride);
+    acc[t] = a;
   }
   if (f.weight) {
     const int o = idx / cin, i = idx - o * cin;
@@ -240,21 +258,50 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int wgrad_slices(int sms, int base_items, int n_ptiles, int cout, int cin, size_t scratch_bytes) {
-  int s = (sms + base_items - 1) / base_items;       // one wave of work items: the finish pass reads every slice
-  s = std::max(1, std::min(std::min(s, 128), n_ptiles));
-  const size_t per_slice = static_cast<size_t>(9) * cout * cin * 4;
-  const size_t cap = scratch_bytes / per_slice;
-  if (cap < 1) return 0;
-  if (static_cast<size_t>(s) > cap) s = static_cast<int>(cap);
-  return s;
+// Pixel slices per tap group, proportional to the group's tap count (equal MMAs per work item) and sized for ONE wave of
+// work items on `sms` SMs (the finish pass reads every slice, so more slices than needed only cost traffic); limited by the
+// number of pixel tiles and by the scratch.  Returns the number of work items, 0 if even one slice per tap does not fit.
+static int wgrad_plan(WgradParams* p, int sms, size_t scratch_bytes) {
+  const int pairs = p->o_tiles * p->i_tiles;
+  int wsum = 0;
+  for (int g = 0; g < p->n_groups; ++g) wsum += p->g[g].ntaps;
+  const size_t slot_bytes = static_cast<size_t>(p->cout) * p->cin * 4;
+  double k = static_cast<double>(sms) / (static_cast<double>(pairs) * wsum);      // slices per tap of weight
+  for (int iter = 0; iter < 64; ++iter, k *= 0.9) {
+    int items = 0, slots = 0;
+    bool all_one = true;
+    for (int g = 0; g < p->n_groups; ++g) {
+      WgradGroup& G = p->g[g];
+      int sl = static_cast<int>(k * G.ntaps);
+      sl = std::max(1, std::min(std::min(sl, 128), p->n_ptiles));
+      G.slices = sl;
+      G.item_base = items;
+      items += pairs * sl;
+      slots += G.ntaps * sl;
+      all_one = all_one && sl == 1;
+    }
+    if ((items <= sms && static_cast<size_t>(slots) * slot_bytes <= scratch_bytes) || all_one) {
+      if (static_cast<size_t>(slots) * slot_bytes > scratch_bytes) return 0;
+      int base = 0;
+      for (int t = 0; t < 9; ++t) p->tap_slices[t] = 0;
+      for (int g = 0; g < p->n_groups; ++g)
+        for (int t = 0; t < p->g[g].ntaps; ++t) p->tap_slices[p->g[g].tap_out[t]] = p->g[g].slices;
+      for (int t = 0; t < 9; ++t) {
+        p->tap_base[t] = base;
+        base += p->tap_slices[t];
+      }
+      p->total_items = items;
+      return items;
+    }
+  }
+  return 0;
 }
 
 size_t wgrad_scratch_bytes(int cout, int cin) {
-  // enough slices for 2 x 148 work items (at most 128 slices; 66 MB on a 512 -> 512 layer)
+  // room for one wave of work items on up to 192 SMs (at most 128 slices per tap; 38 MB on a 512 -> 512 layer)
   const size_t per_slice = static_cast<size_t>(9) * cout * cin * 4;
   const int base = 3 * ((cout + 127) / 128) * std::max(1, cin / 128);
-  const int s = std::max(1, std::min(128, (2 * 148 + base - 1) / base));
+  const int s = std::max(1, std::min(128, (192 + base - 1) / base));
   return per_slice * s;
 }
 
@@ -315,9 +362,8 @@ int wgrad_launch(const sgr_wgrad_args* a, const WgradFinish* finish, cudaStream_
         }
     }
   }
-  const int base_items = p.n_groups * p.o_tiles * p.i_tiles;
-  p.slices = wgrad_slices(sms, base_items, p.n_ptiles, a->cout, a->cin, a->scratch_bytes);
-  if (p.slices < 1) {
+  const int total_items = wgrad_plan(&p, sms, a->scratch_bytes);
+  if (total_items < 1) {
     set_error("modconv_wgrad: scratch too small (%zu bytes, one slice needs %zu)", a->scratch_bytes,
               static_cast<size_t>(9) * a->cout * a->cin * 4);
     return 1;
@@ -344,14 +390,18 @@ int wgrad_launch(const sgr_wgrad_args* a, const WgradFinish* finish, cudaStream_
   const int a_ch = a->up ? 4 * a->cout : a->cout, a_h = a->up ? a->h_in + 1 : a->h_in, a_w = a->up ? a->w_in + 1 : a->w_in;
   if (make_act_tensor_map(&tmap_a, a->gz_c8, a->batch, a_ch, a_h, a_w, abw, abh, 1, 2, 16)) return 1;
   if (make_act_tensor_map(&tmap_b, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw, p.bh, 1, 2, p.nt / 8)) return 1;
-  const int total_items = base_items * p.slices;
   wgrad_kernel<<<std::min(total_items, sms), 256, smem_bytes, stream>>>(tmap_a, tmap_b, p);
   count_launch();
   if (!check_launch("wgrad_kernel")) return 1;
   WgradFinish f;
   memset(&f, 0, sizeof(f));
   if (finish) f = *finish;
-  wgrad_finish_kernel<<<(a->cout * a->cin + 255) / 256, 256, 0, stream>>>(p.part, p.slices, a->cout, a->cin, a->gw, f);
+  WgradSlots slots;
+  for (int t = 0; t < 9; ++t) {
+    slots.base[t] = p.tap_base[t];
+    slots.count[t] = p.tap_slices[t];
+  }
+  wgrad_finish_kernel<<<(a->cout * a->cin + 255) / 256, 256, 0, stream>>>(p.part, slots, a->cout, a->cin, a->gw, f);
   count_launch();
   return check_launch("wgrad_finish_kernel") ? 0 : 1;
 }
