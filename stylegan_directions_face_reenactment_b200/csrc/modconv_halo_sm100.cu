@@ -15,24 +15,33 @@
 // warp1 MMA issuer, warp2 TMEM allocator, warps4-7 epilogue.
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 #include "sgr_internal.h"
 #include "sgr_ptx.cuh"
 #include "modconv_epilogue.cuh"
+#include "fir_producer.cuh"
 
 namespace sgr {
 
-template <int NT, int MT>
+constexpr int kFirRows = 12;      // plane rows m_first-1 .. m_first+10 feed the 18 halo-tile rows (fir_producer.cuh)
+constexpr int kFirWarps = 8;      // fused mode: warps 8..15 build the A halo tiles from the parity planes
+
+template <int NT, int MT, bool FUSED = false>
 struct HaloCfg {
   static constexpr int kTileW = 8 * MT, kTileH = 16;
   static constexpr int kHW = kTileW + 2, kHH = kTileH + 2;
   static constexpr int kChunkBytes = kHW * kHH * 16;          // one 8-channel chunk of the halo box
   static constexpr int kABytes = kChunkBytes * 4 * 2;         // 32 channels x (hi, lo)
   static constexpr int kBBytes = NT * kBlockK * 2 * 2;        // one (block, tap) weight slab, hi + lo
-  static constexpr int kAStages = 3;
-  static constexpr int kBRaw = (226 * 1024 - 1024 - kAStages * kABytes) / kBBytes;
+  // fused mode: two TMA-fed stages of parity planes, 16 channels each: [plane 4][group 4][row 12][col kPC][4 floats]
+  static constexpr int kPC = kHW / 2 + 3;
+  static constexpr int kPlaneStageBytes = kPC * 16 * kFirRows * 4 * 4;
+  static constexpr int kPlaneBytes = FUSED ? 2 * kPlaneStageBytes : 0;
+  static constexpr int kAStages = FUSED ? 2 : 3;
+  static constexpr int kBRaw = (226 * 1024 - 1024 - kAStages * kABytes - kPlaneBytes) / kBBytes;
   static constexpr int kBStages = kBRaw > 8 ? 8 : kBRaw;
-  static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kBStages * kBBytes;
+  static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kBStages * kBBytes + kPlaneBytes;
   static_assert(kABytes % 128 == 0, "TMA destination alignment");
   static_assert(kBStages >= 3, "weight ring too shallow");
   // NT <= 64: an N = 64 MMA costs as much as N = 128 (the 128-row A operand read bounds it), so the three products of the
@@ -41,12 +50,14 @@ struct HaloCfg {
   static constexpr bool kConcat = NT <= 64;
   static constexpr int kAccCols = kConcat ? 2 * NT : NT;      // TMEM columns per sub-tile
   static_assert(2 * MT * kAccCols <= 512, "TMEM columns");
+  static_assert(kHH == 18, "fir_produce_chunk walks 10 plane rows in two halves of five");
 };
 
-template <int NT, int MT>
-__global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                              const ConvKernelParams p) {
-  using Cfg = HaloCfg<NT, MT>;
+template <int NT, int MT, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                            const __grid_constant__ CUtensorMap tmap_planes,
+                                                                            const ConvKernelParams p, const FusedFirParams f) {
+  using Cfg = HaloCfg<NT, MT, FUSED>;
   constexpr int AS = Cfg::kAStages, BS = Cfg::kBStages;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -56,16 +67,23 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
   uint64_t* tfull = b_empty + BS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* fir_sc = reinterpret_cast<float*>(tmem_slot + 2);      // fused mode: separable FIR taps (gy | gx)
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(fir_sc + 8);   // fused mode: parity-plane stages
+  uint64_t* p_empty = p_full + 2;
   uint8_t* a_base = smem + 1024;
   uint8_t* b_base = a_base + AS * Cfg::kABytes;
+  uint8_t* plane_base = b_base + BS * Cfg::kBBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    if (FUSED) tma_prefetch_desc(&tmap_planes);
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < AS; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], FUSED ? kFirWarps : 1);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < BS; ++i) {
@@ -75,12 +93,27 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
+      if (FUSED) {
+        mbar_init(&p_full[i], 1);
+        mbar_init(&p_empty[i], kFirWarps);
+      }
     }
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if (FUSED && warp == 3 && lane < 4) {      // gy (vertical taps, flipped), gx (horizontal, flipped, / tap sum): up_finish_kernel
+    const int a = lane;
+    float rs = 0.f, cs = 0.f, tot = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      rs += __ldg(f.fir + (3 - a) * 4 + i);
+      cs += __ldg(f.fir + i * 4 + (3 - a));
+      for (int j = 0; j < 4; ++j) tot += __ldg(f.fir + i * 4 + j);
+    }
+    fir_sc[a] = rs;
+    fir_sc[4 + a] = cs / tot;
   }
   tc_fence_before();
   __syncthreads();
@@ -89,6 +122,76 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
 
   const int out_tiles = p.m_tiles * p.n_tiles;
   const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice of channel blocks)
+
+  if (FUSED && warp >= 8) {
+    // ------------------------------------------------------------------ FIR producers (fused mode; ksplit == 1)
+    // every 32-channel block is built in two phases of 16 channels (plane stage h = phase): all eight warps work on the
+    // same stage — chunk (8 channels) = pw & 1, plane-row quarter = pw >> 1 — while TMA refills the other one
+    const int pw = warp - 8, cc = pw & 1, rq = pw >> 1;
+    const int row0 = rq < 2 ? rq * 3 : 2 + rq * 2;               // quarters of the 10 plane rows: 3 + 3 + 2 + 2
+    const int iters = rq < 2 ? 3 : 2;
+    uint32_t ai = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile / p.m_tiles;
+      int m = tile - n_tile * p.m_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int b = m / p.tiles_y;
+      const int X0 = tx * Cfg::kTileW - 1, Y0 = ty * Cfg::kTileH - 1;
+      const int m_first = (Y0 - 1) >> 1;
+      for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+        const uint32_t as = ai % AS;
+        mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);      // (one polling lane + __syncwarp measured 2x SLOWER)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[h], ai & 1);
+          if (p.debug & 512) {                                             // experiment: handshakes only, no FIR work
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_empty[h]);
+            continue;
+          }
+          const uint8_t* stage = plane_base + h * Cfg::kPlaneStageBytes;
+          uint8_t* dst = a_base + as * Cfg::kABytes + (h * 2 + cc) * Cfg::kChunkBytes;
+          const int chunk = kb * 4 + h * 2 + cc;
+          if (p.fmt == kFmtBF16)
+            fir_produce_chunk_smem<Cfg::kHW, Cfg::kHH, kFmtBF16, Cfg::kPC>(f, fir_sc, b, chunk, Y0, X0, stage, cc * 2, m_first + row0,
+                                                                           1 + row0, iters, dst, Cfg::kChunkBytes * 4, lane);
+          else
+            fir_produce_chunk_smem<Cfg::kHW, Cfg::kHH, kFmtFP16, Cfg::kPC>(f, fir_sc, b, chunk, Y0, X0, stage, cc * 2, m_first + row0,
+                                                                           1 + row0, iters, dst, Cfg::kChunkBytes * 4, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_empty[h]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+      }
+    }
+  } else if (FUSED && warp == 3) {
+    // ------------------------------------------------------------------ parity-plane TMA issuer (fused mode)
+    if (lane == 0) {
+      uint32_t ai = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / p.m_tiles;
+        int m = tile - n_tile * p.m_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int b = m / p.tiles_y;
+        const int n_first = (tx * Cfg::kTileW - 2) >> 1, m_first = (ty * Cfg::kTileH - 2) >> 1;
+        for (int kb = 0; kb < p.kchunks; ++kb, ++ai) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&p_empty[h], (ai & 1) ^ 1);
+            mbar_expect_tx(&p_full[h], Cfg::kPlaneStageBytes);
+            tma_load_5d(plane_base + h * Cfg::kPlaneStageBytes, &tmap_planes, &p_full[h], (n_first - 1) * 4, m_first - 1,
+                        kb * 8 + h * 4, 0, b);
+          }
+        }
+      }
+    }
+  } else
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -110,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
         const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         for (int kb = kb0; kb < kb1; ++kb, ++ai) {
           const uint32_t as = ai % AS;
-          if (!(p.debug & 16) || ai < AS) {     // experiment 16: A ring loaded once
+          if (!FUSED && (!(p.debug & 16) || ai < AS)) {     // experiment 16: A ring loaded once; fused: FIR warps fill it
             mbar_wait(&a_empty[as], ((ai / AS) & 1) ^ 1);
             mbar_expect_tx(&a_full[as], a_bytes);
             tma_load_5d(a_base + as * Cfg::kABytes, &tmap, &a_full[as], x0 * 8, y0, b, kb * 4, 0);
@@ -273,12 +376,13 @@ __global__ void __launch_bounds__(256, 1) modconv_halo_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int NT, int MT>
-static int launch_halo(const ConvKernelParams& p, const CUtensorMap& tmap, int sms, cudaStream_t stream) {
-  using Cfg = HaloCfg<NT, MT>;
+template <int NT, int MT, bool FUSED>
+static int launch_halo_impl(const ConvKernelParams& p, const CUtensorMap& tmap, int sms, cudaStream_t stream,
+                            const FusedFirParams& f) {
+  using Cfg = HaloCfg<NT, MT, FUSED>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(modconv_halo_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(modconv_halo_kernel<NT, MT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("modconv_halo: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -287,9 +391,20 @@ static int launch_halo(const ConvKernelParams& p, const CUtensorMap& tmap, int s
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
-  modconv_halo_kernel<NT, MT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, p);
+  CUtensorMap tmap_planes = tmap;            // not fused: unused placeholder
+  if (FUSED && make_plane_tensor_map(&tmap_planes, f.t, p.B, f.C, f.Hin + 1, f.Win + 1, Cfg::kPC)) return 1;
+  modconv_halo_kernel<NT, MT, FUSED><<<std::min(total, sms), FUSED ? 512 : 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_planes, p, f);
   count_launch();
   return check_launch("modconv_halo_kernel") ? 0 : 1;
+}
+
+template <int NT, int MT>
+static int launch_halo(const ConvKernelParams& p, const CUtensorMap& tmap, int sms, cudaStream_t stream,
+                       const FusedFirParams* fused) {
+  if (fused) return launch_halo_impl<NT, MT, true>(p, tmap, sms, stream, *fused);
+  FusedFirParams none;
+  memset(&none, 0, sizeof(none));
+  return launch_halo_impl<NT, MT, false>(p, tmap, sms, stream, none);
 }
 
 bool halo_eligible(const sgr_conv_args* a) {
@@ -299,7 +414,18 @@ bool halo_eligible(const sgr_conv_args* a) {
 }
 
 // Fills the tile geometry of `p` (already filled by conv_fill_params) for the halo kernel and launches it.
-int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream) {
+// A halo convolution can take its input straight from the parity planes of the preceding scatter up-conv (fused FIR
+// producer warps) when nothing else needs that activation: fp32-parity mode, no split-K, channel blocks of 32.
+// EXPERIMENTAL, off by default (SGR_FUSE_FIR=1): parity-green, removes the FIR pass (0.51 ms of a 3.40 ms step at B=32,
+// 256^2) and its 2.1 GB of traffic, but the eight producer warps need ~50 % of the SM's issue slots and slow the consumers by
+// 0.55 ms in total (3.43 vs 3.38 ms); with the FIR work switched off (SGR_DEBUG=512, handshakes only) the step is 2.96 ms —
+// the bound a cheaper producer could approach.
+bool halo_fusable(const sgr_conv_args* a) {
+  static const bool on = [] { const char* e = getenv("SGR_FUSE_FIR"); return e && e[0] == '1'; }();
+  return on && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0;
+}
+
+int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream, const FusedFirParams* fused) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
@@ -316,15 +442,15 @@ int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t
   p.n_tiles = a->cout / nt;
   p.halo_mt = mt;
   p.nt = nt;
-  set_ksplit(&p, choose_ksplit(a, p.m_tiles * p.n_tiles, p.kchunks, 2, static_cast<size_t>(mt) * kTileM * nt * 4));
+  set_ksplit(&p, fused ? 1 : choose_ksplit(a, p.m_tiles * p.n_tiles, p.kchunks, 2, static_cast<size_t>(mt) * kTileM * nt * 4));
   CUtensorMap tmap;
   if (make_act_tensor_map(&tmap, a->x_c8, a->batch, a->cin, a->h_in, a->w_in, p.bw + 2, p.bh + 2, 1, p.single ? 1 : 2)) return 1;
   int rc;
   switch (nt) {
-    case 256: rc = launch_halo<256, 1>(p, tmap, sms, stream); break;
-    case 128: rc = launch_halo<128, 2>(p, tmap, sms, stream); break;
-    case 64: rc = launch_halo<64, 2>(p, tmap, sms, stream); break;
-    case 32: rc = launch_halo<32, 2>(p, tmap, sms, stream); break;
+    case 256: rc = launch_halo<256, 1>(p, tmap, sms, stream, fused); break;
+    case 128: rc = launch_halo<128, 2>(p, tmap, sms, stream, fused); break;
+    case 64: rc = launch_halo<64, 2>(p, tmap, sms, stream, fused); break;
+    case 32: rc = launch_halo<32, 2>(p, tmap, sms, stream, fused); break;
     default: set_error("modconv_halo: unsupported column tile %d", nt); return 1;
   }
   if (rc == 0 && p.ksplit > 1) rc = splitk_finish_launch(p, stream);

@@ -228,17 +228,44 @@ int sgr_nchw_to_c8(const float* x, const float* scale, void* out_c8, int batch, 
   return nchw_to_c8_launch(x, scale, out_c8, batch, channels, h, w, s2d, format, static_cast<cudaStream_t>(stream));
 }
 
-int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
+// plane scales of the FIR pass of an up == 2 layer: undo the operand scales, compensate the accumulate truncation
+static void up_plane_scales(const sgr_conv_args* args, float* base, float* comp) {
+  *base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
+  *comp = acc_comp_enabled() ? 1.16e-8f * (args->single_pass ? 1.f : 3.f) * static_cast<float>(args->cin / 16) : 0.f;
+}
+
+// The FIR pass of up-layer `up` expressed as the producer of the following halo convolution (fir_producer.cuh).
+static void fill_fused_fir(const sgr_conv_args* up, FusedFirParams* f) {
+  memset(f, 0, sizeof(*f));
+  float base, comp;
+  up_plane_scales(up, &base, &comp);
+  const int taps[4] = {2, 4, 2, 1};                  // MMA chains accumulated per plane: oe, ee, eo, oo (up_finish_launch)
+  for (int i = 0; i < 4; ++i) f->plane_scale[i] = base * (1.f + comp * taps[i]);
+  f->t = up->t_scratch; f->fir = up->fir;
+  f->C = up->cout; f->Hin = up->h_in; f->Win = up->w_in;
+  f->demod = up->demod; f->bias = up->bias;
+  f->noise = up->noise; f->noise_bstride = up->noise_batch_stride; f->noise_w = up->noise_weight;
+  f->s2 = up->s2; f->act = up->act; f->act_gain = up->act_gain; f->out_scale = act_scale(up->out_format);
+}
+
+// defer_fir: (up == 2) run the scatter GEMM only; the consumer applies the FIR pass (fused_src = that layer's arguments)
+static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* fused_src, bool defer_fir, void* stream) {
   if (!have_device()) return 1;
   ConvKernelParams p;
   int nt = 0;
   if (conv_fill_params(args, &p, &nt)) return 1;
   int rc;
   if (halo_eligible(args)) {           // wide 3x3 layers: resident halo tile (modconv_halo_sm100.cu)
+    FusedFirParams f;
+    if (fused_src) fill_fused_fir(fused_src, &f);
     const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
-    rc = launch_modconv_halo(args, p, static_cast<cudaStream_t>(stream));
+    rc = launch_modconv_halo(args, p, static_cast<cudaStream_t>(stream), fused_src ? &f : nullptr);
     if (prof) prof_end(static_cast<cudaStream_t>(stream));
     return rc;
+  }
+  if (fused_src) {
+    set_error("modconv_forward: fused FIR input needs a halo-eligible layer");
+    return 1;
   }
   CUtensorMap tmap;
   if (args->up == 3) {       // gather adjoint: the operand is the 4-plane tensor on the (h+1) x (w+1) grid
@@ -256,15 +283,17 @@ int sgr_modconv_forward(const sgr_conv_args* args, void* stream) {
                      : launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
   if (rc == 0 && p.ksplit > 1) rc = splitk_finish_launch(p, static_cast<cudaStream_t>(stream));
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
-  if (rc == 0 && args->up == 2) {
-    const float base = 1.f / (act_scale(args->operand_format) * w_scale(args->operand_format));
-    const float comp = acc_comp_enabled() ? 1.16e-8f * (args->single_pass ? 1.f : 3.f) * static_cast<float>(args->cin / 16) : 0.f;
+  if (rc == 0 && args->up == 2 && !defer_fir) {
+    float base, comp;
+    up_plane_scales(args, &base, &comp);
     const bool prof2 = prof_begin(static_cast<cudaStream_t>(stream), 1);
     rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream));
     if (prof2) prof_end(static_cast<cudaStream_t>(stream));
   }
   return rc;
 }
+
+int sgr_modconv_forward(const sgr_conv_args* args, void* stream) { return modconv_forward_impl(args, nullptr, false, stream); }
 
 void sgr_profile_enable(int on) { g_prof_on = on != 0; }
 
@@ -374,6 +403,8 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
   int res = 4;
   int skip_cur = 0;
   const float* prev_skip = nullptr;
+  sgr_conv_args pending_up;                 // an up layer whose FIR pass the next convolution applies (fused producer)
+  bool have_pending = false;
   for (int l = 0; l < net->n_styled; ++l) {
     const sgr_styled_layer& L = net->styled[l];
     const bool last = l + 1 == net->n_styled;
@@ -416,7 +447,17 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
       a.fir = L.fir;
       a.t_scratch = F(pl.t_off);
     }
-    if (sgr_modconv_forward(&a, stream)) return 1;
+    bool defer = false;
+    if (L.up == 2 && !last && !a.out_f32 && net->styled[l + 1].up == 0) {
+      sgr_conv_args nx;                      // the consumer, as far as halo_fusable() looks at it
+      memset(&nx, 0, sizeof(nx));
+      nx.batch = batch; nx.cin = L.cout; nx.cout = net->styled[l + 1].cout; nx.h_in = nx.w_in = 2 * res; nx.ksize = 3;
+      nx.single_pass = net->single_pass;
+      defer = halo_fusable(&nx);
+    }
+    if (modconv_forward_impl(&a, have_pending ? &pending_up : nullptr, defer, stream)) return 1;
+    have_pending = defer;
+    if (defer) pending_up = a;
     if (L.up) res *= 2;
     cur = 1 - cur;
     if (!L.up) {

@@ -79,12 +79,30 @@ struct ConvKernelParams {
   float acc_base, acc_mmas;     // acc_scale = acc_base * (1 + 1.16e-8 * acc_mmas / ksplit)
 };
 
+// FIR pass of the preceding scatter up-conv folded into a halo convolution's producer warps (fir_producer.cuh)
+struct FusedFirParams {
+  const float* t;               // [B][4 (oe,ee,eo,oo)][C/4][Hin+1][Win+1][4] fp32 parity planes
+  const float* fir;             // [4][4] blur.kernel
+  int C, Hin, Win;              // the up layer's output channels (= this conv's cin) and INPUT resolution
+  float plane_scale[4];
+  const float* demod;           // [B,C] of the up layer
+  const float* bias;            // [C] or NULL
+  const float* noise;           // [2Hin,2Win] (+ batch stride) or NULL
+  long long noise_bstride;
+  const float* noise_w;
+  const float* s2;              // [B,C]: sqrt2 * this conv's style
+  int act;
+  float act_gain, out_scale;
+};
+
 // modconv_sm100.cu
 int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // host: build the 5-D tensor map over C8 activation planes
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
                         int bb, int planes = 2, int chunk_box = kBlockK / 8);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
+// 5-D map over fp32 parity planes [B][4][C/4][Hp][Wp][4]: box = (cols x 4 floats, 12 rows, 4 groups, 4 planes, 1 sample)
+int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int channels, int hp, int wp, int cols);
 int num_sms();
 // modconv_scatter_sm100.cu: scatter-form upsampling convolution (parity planes -> p.t_out)
 int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
@@ -95,7 +113,8 @@ constexpr size_t kSplitKScratchBytes = 160u * 128u * 1024u;      // >= 148 CTA t
 int choose_ksplit(const sgr_conv_args* a, int tiles, int k_units, int min_units_per_slice, size_t tile_bytes);
 void set_ksplit(ConvKernelParams* p, int ksplit);
 int splitk_finish_launch(const ConvKernelParams& p, cudaStream_t stream);
-int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream);
+int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream, const FusedFirParams* fused = nullptr);
+bool halo_fusable(const sgr_conv_args* a);
 
 // wgrad_sm100.cu: weight-gradient GEMM (K = pixels, MN-major operands)
 size_t wgrad_scratch_bytes(int cout, int cin);
