@@ -35,7 +35,10 @@ struct HaloCfg {
   static constexpr int kABytes = kChunkBytes * 4 * 2;         // 32 channels x (hi, lo)
   static constexpr int kBBytes = NT * kBlockK * 2 * 2;        // one (block, tap) weight slab, hi + lo
   // fused mode: two TMA-fed stages of parity planes, 16 channels each: [plane 4][group 4][row 12][col kPC][4 floats]
-  static constexpr int kPC = kHW / 2 + 3;
+  // plane-window columns: kHW / 2 + 3 are needed; the 18-pixel tile takes 13 so that the three row sub-groups of a producer
+  // warp (rows 384 B apart at 12 columns = the same banks) fall into different banks (ncu: 50 % of the wavefronts conflicted)
+  // (the 10-pixel tile: five sub-groups of six lanes, rows one apart: 14 columns = 224 B pitch)
+  static constexpr int kPC = kHW == 18 ? 13 : 14;
   static constexpr int kPlaneStageBytes = kPC * 16 * kFirRows * 4 * 4;
   static constexpr int kPlaneBytes = FUSED ? 2 * kPlaneStageBytes : 0;
   static constexpr int kAStages = FUSED ? 2 : 3;
@@ -125,11 +128,9 @@ __global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(cons
 
   if (FUSED && warp >= 8) {
     // ------------------------------------------------------------------ FIR producers (fused mode; ksplit == 1)
-    // every 32-channel block is built in two phases of 16 channels (plane stage h = phase): all eight warps work on the
-    // same stage — chunk (8 channels) = pw & 1, plane-row quarter = pw >> 1 — while TMA refills the other one
-    const int pw = warp - 8, cc = pw & 1, rq = pw >> 1;
-    const int row0 = rq < 2 ? rq * 3 : 2 + rq * 2;               // quarters of the 10 plane rows: 3 + 3 + 2 + 2
-    const int iters = rq < 2 ? 3 : 2;
+    // every 32-channel block is built in two phases of 16 channels (plane stage h = phase): all eight warps work on the same
+    // stage — 4-channel group = pw >> 1, upper / lower five plane rows = pw & 1 — while TMA refills the other one
+    const int pw = warp - 8, gq = pw >> 1, rhalf = pw & 1;
     uint32_t ai = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile / p.m_tiles;
@@ -146,20 +147,18 @@ __global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(cons
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&p_full[h], ai & 1);
-          if (p.debug & 512) {                                             // experiment: handshakes only, no FIR work
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_empty[h]);
-            continue;
+          if (!(p.debug & 512)) {                                          // experiment 512: handshakes only, no FIR work
+            const uint8_t* stage = plane_base + h * Cfg::kPlaneStageBytes;
+            // group gq of this stage = channels kb*32 + h*16 + gq*4 ..: chunk h*2 + (gq >> 1), upper half when gq is odd
+            uint8_t* dst8 = a_base + as * Cfg::kABytes + (h * 2 + (gq >> 1)) * Cfg::kChunkBytes + (gq & 1) * 8;
+            const int group = kb * 8 + h * 4 + gq;
+            if (p.fmt == kFmtBF16)
+              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtBF16, Cfg::kPC>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + rhalf * 5,
+                                                                             1 + rhalf * 5, dst8, Cfg::kChunkBytes * 4, lane);
+            else
+              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtFP16, Cfg::kPC>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + rhalf * 5,
+                                                                             1 + rhalf * 5, dst8, Cfg::kChunkBytes * 4, lane);
           }
-          const uint8_t* stage = plane_base + h * Cfg::kPlaneStageBytes;
-          uint8_t* dst = a_base + as * Cfg::kABytes + (h * 2 + cc) * Cfg::kChunkBytes;
-          const int chunk = kb * 4 + h * 2 + cc;
-          if (p.fmt == kFmtBF16)
-            fir_produce_chunk_smem<Cfg::kHW, Cfg::kHH, kFmtBF16, Cfg::kPC>(f, fir_sc, b, chunk, Y0, X0, stage, cc * 2, m_first + row0,
-                                                                           1 + row0, iters, dst, Cfg::kChunkBytes * 4, lane);
-          else
-            fir_produce_chunk_smem<Cfg::kHW, Cfg::kHH, kFmtFP16, Cfg::kPC>(f, fir_sc, b, chunk, Y0, X0, stage, cc * 2, m_first + row0,
-                                                                           1 + row0, iters, dst, Cfg::kChunkBytes * 4, lane);
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_empty[h]);
         }

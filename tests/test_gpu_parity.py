@@ -262,6 +262,39 @@ def test_reenact_from_files(pkg, golden, tmp_path):
     assert err(img, g['img']) <= 1e-3
 
 
+def test_fused_fir_producer_mode_matches_default(pkg, tmp_path):
+    """Experimental SGR_FUSE_FIR=1 (FIR pass of the up layers applied by producer warps of the following convolution,
+    csrc/fir_producer.cuh): same image as the default two-kernel path to accumulate-rounding level, and within the 1e-3 bar of
+    the oracle.  The switch is read once per process, so the fused run is a subprocess."""
+    import os
+    import subprocess
+    import sys
+    size, cm, batch = 64, 2, 3
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / 'fused.npy')
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from oracle import stylegan2_oracle as orc\n"
+            "import stylegan_directions_face_reenactment_b200 as pkg\n"
+            "sd = orc.seeded_state_dict(%d, %d, seed=6)\n"
+            "G = pkg.Generator(%d, 512, 8, channel_multiplier=%d); G.load_state_dict(sd, strict=True); G = G.cuda().eval()\n"
+            "w = orc.seeded_wplus(sd, %d, G.n_latent, seed=9).cuda()\n"
+            "with torch.no_grad(): img = G([w], input_is_latent=True)[0]\n"
+            "np.save(%r, img.cpu().numpy())\n") % (root, size, cm, size, cm, batch, out)
+    env = dict(os.environ, SGR_FUSE_FIR='1')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=300)
+    fused = np.load(out)
+    sd = orc.seeded_state_dict(size, cm, seed=6)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, batch, G.n_latent, seed=9)
+    with torch.no_grad():
+        img = G([wplus.cuda()], input_is_latent=True)[0]
+        ref, _ = orc.generator_forward(sd, [wplus], size, cm, input_is_latent=True)
+    assert err(img, fused) <= 2e-4
+    assert float(np.abs(fused - ref.numpy()).max()) <= 1e-3
+
+
 def test_weight_cache_invalidation(pkg):
     size, cm = 8, 2
     sd = orc.seeded_state_dict(size, cm, seed=8)
