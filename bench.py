@@ -348,9 +348,14 @@ def main():
         fin_bytes = 0
         from oracle import stylegan2_oracle as orc
         channels, log_size, _, _ = orc.synthesis_config(SIZE, CM)
+        up_bytes = []
         for i in range(3, log_size + 1):
             cout, h = channels[2 ** i], 2 ** (i - 1)
-            fin_bytes += BATCH * cout * (4 * (h + 1) ** 2 * 4 + (2 * h) ** 2 * 4)
+            up_bytes.append(BATCH * cout * (4 * (h + 1) ** 2 * 4 + (2 * h) ** 2 * 4))
+        # the FIR pass of an up layer whose consumer is a resident-halo convolution (16^2 and larger) is applied by that
+        # convolution's producer warps (csrc/fir_producer.cuh; SGR_FUSE_FIR=0 disables): only the first fin_per_step
+        # (smallest) up layers still launch the separate pass
+        fin_bytes = sum(up_bytes[:fin_per_step])
         roofline = {'bound': 'tensor',
                     'kernel': 'tcgen05 conv kernels: modconv / modconv_halo / upconv_scatter (%d launches/step)' % per_step,
                     'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
@@ -360,7 +365,9 @@ def main():
                             'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
                             'comparable to the bf16 dense peak',
                     'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps),
-                    'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step)' % fin_per_step, 'bound': 'hbm',
+                    'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step; %d up layers have their FIR pass fused into '
+                                           'the consumer convolution)' % (fin_per_step, len(up_bytes) - fin_per_step),
+                                 'bound': 'hbm',
                                  'ms_per_step': fin_total, 'algorithmic_bytes': fin_bytes,
                                  'achieved': fin_bytes / (fin_total * 1e-3) / 1e9 if fin_total > 0 else None,
                                  'peak': pk['hbm'], 'unit': 'GB/s',

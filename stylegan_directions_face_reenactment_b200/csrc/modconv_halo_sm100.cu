@@ -415,13 +415,18 @@ bool halo_eligible(const sgr_conv_args* a) {
 // Fills the tile geometry of `p` (already filled by conv_fill_params) for the halo kernel and launches it.
 // A halo convolution can take its input straight from the parity planes of the preceding scatter up-conv (fused FIR
 // producer warps) when nothing else needs that activation: fp32-parity mode, no split-K, channel blocks of 32.
-// EXPERIMENTAL, off by default (SGR_FUSE_FIR=1): parity-green, removes the FIR pass (0.51 ms of a 3.40 ms step at B=32,
-// 256^2) and its 2.1 GB of traffic, but the eight producer warps need ~50 % of the SM's issue slots and slow the consumers by
-// 0.55 ms in total (3.43 vs 3.38 ms); with the FIR work switched off (SGR_DEBUG=512, handshakes only) the step is 2.96 ms —
-// the bound a cheaper producer could approach.
+// On by default (SGR_FUSE_FIR=0 restores the separate up_finish_kernel pass): removes the FIR pass (0.51 ms of a 3.40 ms
+// step at B=32, 256^2) and 2.1 GB of its traffic; the eight producer warps cost the five consumers 0.33 ms in total (shared-
+// memory bandwidth: MMA operand reads + producer loads run at ~125 of 128 B/clk), net 3.22 vs 3.40 ms.  With the FIR work
+// switched off (SGR_DEBUG=512, handshakes only) the step is 2.96 ms, the bound a cheaper producer can approach.
 bool halo_fusable(const sgr_conv_args* a) {
-  static const bool on = [] { const char* e = getenv("SGR_FUSE_FIR"); return e && e[0] == '1'; }();
-  return on && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0;
+  static const bool on = [] { const char* e = getenv("SGR_FUSE_FIR"); return !(e && e[0] == '0'); }();
+  if (!(on && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0)) return false;
+  // layers with fewer tiles than half the SMs (small batches) run split-K, which the fused producers do not support
+  const int nt = a->column_tile > 0 ? a->column_tile : pick_nt(a->cout);
+  const int mt = nt <= 128 ? 2 : 1;
+  const int tiles = ((a->w_in + 8 * mt - 1) / (8 * mt)) * ((a->h_in + 15) / 16) * a->batch * (a->cout / nt);
+  return 2 * tiles > num_sms();
 }
 
 int launch_modconv_halo(const sgr_conv_args* a, ConvKernelParams p, cudaStream_t stream, const FusedFirParams* fused) {

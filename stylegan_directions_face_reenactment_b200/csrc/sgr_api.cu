@@ -453,6 +453,7 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
       memset(&nx, 0, sizeof(nx));
       nx.batch = batch; nx.cin = L.cout; nx.cout = net->styled[l + 1].cout; nx.h_in = nx.w_in = 2 * res; nx.ksize = 3;
       nx.single_pass = net->single_pass;
+      nx.column_tile = net->styled[l + 1].column_tile;
       defer = halo_fusable(&nx);
     }
     if (modconv_forward_impl(&a, have_pending ? &pending_up : nullptr, defer, stream)) return 1;

@@ -262,10 +262,10 @@ def test_reenact_from_files(pkg, golden, tmp_path):
     assert err(img, g['img']) <= 1e-3
 
 
-def test_fused_fir_producer_mode_matches_default(pkg, tmp_path):
-    """Experimental SGR_FUSE_FIR=1 (FIR pass of the up layers applied by producer warps of the following convolution,
-    csrc/fir_producer.cuh): same image as the default two-kernel path to accumulate-rounding level, and within the 1e-3 bar of
-    the oracle.  The switch is read once per process, so the fused run is a subprocess."""
+def test_fused_fir_producer_mode_matches_separate_pass(pkg, tmp_path):
+    """The FIR pass of the up layers applied by producer warps of the following convolution (csrc/fir_producer.cuh, the
+    default) against the separate up_finish_kernel pass (SGR_FUSE_FIR=0): same image to accumulate-rounding level, both within
+    the 1e-3 bar of the oracle.  The switch is read once per process, so the other mode runs in a subprocess."""
     import os
     import subprocess
     import sys
@@ -280,7 +280,7 @@ def test_fused_fir_producer_mode_matches_default(pkg, tmp_path):
             "w = orc.seeded_wplus(sd, %d, G.n_latent, seed=9).cuda()\n"
             "with torch.no_grad(): img = G([w], input_is_latent=True)[0]\n"
             "np.save(%r, img.cpu().numpy())\n") % (root, size, cm, size, cm, batch, out)
-    env = dict(os.environ, SGR_FUSE_FIR='1')
+    env = dict(os.environ, SGR_FUSE_FIR='0' if os.environ.get('SGR_FUSE_FIR', '1') != '0' else '1')
     subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=300)
     fused = np.load(out)
     sd = orc.seeded_state_dict(size, cm, seed=6)
