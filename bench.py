@@ -365,6 +365,10 @@ def main():
                             'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
                             'comparable to the bf16 dense peak',
                     'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps),
+                    'fused_fir_note': 'the convolution launches that follow an up layer also apply that layer\'s 4x4 FIR + '
+                                      'epilogue pass in producer warps (csrc/fir_producer.cuh), so their duration includes it; '
+                                      'SGR_FUSE_FIR=0 separates the pass again (conv kernels 8 % faster, step 5 % slower)',
+                    'step_algorithmic_tflops': total_fl / (ms / args.steps * 1e-3) / 1e12,
                     'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step; %d up layers have their FIR pass fused into '
                                            'the consumer convolution)' % (fin_per_step, len(up_bytes) - fin_per_step),
                                  'bound': 'hbm',
@@ -374,6 +378,25 @@ def main():
                                  'frac': fin_bytes / (fin_total * 1e-3) / 1e9 / pk['hbm'] if fin_total > 0 else None}}
         layers = [{'layer': l, 'ms': round(d, 4), 'algo_tflops': round(f * BATCH / (d * 1e-3) / 1e12, 2)}
                   for l, (d, f) in enumerate(zip(dur, fl))]
+        if fin_per_step < len(up_bytes):
+            roofline['hbm_pass']['note'] = ('only the smallest up layers still run the separate pass (launch-latency bound at '
+                                            'this size); the others are fused into their consumer, see fused_fir_note')
+        # the same measurement with the FIR pass as a separate kernel (the GEMM kernels alone), in a child process: the
+        # switch is read once per process
+        if world == 1 and os.environ.get('SGR_FUSE_FIR', '1') != '0' and not os.environ.get('SGR_BENCH_CHILD'):
+            import subprocess
+            try:
+                env = dict(os.environ, SGR_FUSE_FIR='0', SGR_BENCH_CHILD='1')
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--steps', '10', '--warmup', '3',
+                                      '--cpu-baseline', '0'], env=env, capture_output=True, text=True, timeout=300).stdout
+                ch = json.loads(out.strip().splitlines()[-1])
+                roofline['separate_fir_pass'] = {
+                    'ms_per_step': ch['ms_per_step'], 'value': ch['value'], 'conv_kernel_ms_per_step': ch['roofline']['kernel_ms_per_step'],
+                    'achieved': ch['roofline']['achieved'], 'frac': ch['roofline']['frac'], 'issued_frac': ch['roofline']['issued_frac'],
+                    'hbm_pass': ch['roofline']['hbm_pass'],
+                    'note': 'SGR_FUSE_FIR=0: GEMM kernels without the fused FIR producers + the HBM-bound up_finish_kernel pass'}
+            except Exception as e:  # noqa: BLE001  (informational leg only)
+                roofline['separate_fir_pass'] = {'error': str(e)[:200]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_baseline:
