@@ -18,7 +18,9 @@
 // operands: the xs tile is loaded unshifted and the gz box carries the halo, a tap is a start-address offset into it.
 // A work item = (tap group, 128-channel row tile, NT-channel column tile, slice of the pixel tiles); a tap group shares
 // one gz box (plain: the three kx of a kernel row; up: the taps of one parity plane) and owns one TMEM accumulator per
-// tap.  Slices write fp32 partials and wgrad_finish_kernel adds them in slice order (deterministic, no atomics).
+// tap.  The work items are planned as ONE wave of equal-work items: the pixel tiles of a tap group are cut into a number of
+// slices proportional to its taps (wgrad_plan).  Slices write fp32 partials and wgrad_finish_kernel adds them in slice order
+// (deterministic, no atomics).
 // fp32 parity: bf16 hi/lo operands, three MMAs per product, like every other gradient GEMM of the library.
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over work items): warp0 TMA producer, warp1 MMA issuer, warp2 TMEM
