@@ -45,7 +45,7 @@ __device__ __forceinline__ void fir_split_pair(float v0, float v1, int fmt, uint
 // Shuffle-free mapping (the first version used up_finish_kernel's: 16 columns per half-warp with halo lanes and shuffles
 // for the horizontal taps — 62 % of the lanes productive, 1.6x the instructions): the warp handles ONE 4-channel group and
 // five plane rows; lane = (producing plane
-// column c, row sub-group): kCols x RS lanes (10 x 3 or 6 x 5 of 32) each walk 1-2 plane rows.  The FIR runs horizontally
+// column c, row sub-group): kCols x RS lanes (10 x 3 or 6 x 5 of 32) each walk 1-2 of the task's `nrows` plane rows.  The FIR runs horizontally
 // first — every lane reads its three plane columns straight from the staged planes, so there are no halo lanes and no
 // warp-collective operations — then vertically over a register window of the row results.
 //   He_r(px0) = gx3 ee[r][n+1] + gx2 eo[r][n] + gx1 ee[r][n] + gx0 eo[r][n-1]      (even plane rows; px0: X = 2n)
@@ -57,18 +57,19 @@ struct FH {          // row result of one row parity: two pixels x 4 channels
   FP4 p0, p1;
 };
 
-template <int kHW, int kHH, int FMT, int PC>
+template <int kHW, int kHH, int FMT, int PC, int NR_MAX>
 __device__ __forceinline__ void fir_produce_group_smem(const FusedFirParams& f, const float* sc, int b, int group, int Y0, int X0,
-                                                       const uint8_t* stage, int g_in_stage, int m_h, int r_h, uint8_t* dst8,
-                                                       uint32_t lo_off, int lane) {
+                                                       const uint8_t* stage, int g_in_stage, int m_h, int r_h, int nrows,
+                                                       uint8_t* dst8, uint32_t lo_off, int lane) {
   constexpr int kCols = kHW / 2 + 1;
   constexpr int RS = 32 / kCols;
   static_assert(PC >= kCols + 2, "plane window columns");
   const int c = lane % kCols, rsub = lane / kCols;
   if (rsub >= RS) return;                                     // spare lanes: nothing below is warp-collective
-  constexpr int kBase = 5 / RS, kRem = 5 % RS;
-  const int row_off = rsub * kBase + min(rsub, kRem);
-  const int cnt = kBase + (rsub < kRem ? 1 : 0);
+  constexpr int kMaxCnt = (NR_MAX + RS - 1) / RS;             // plane rows per lane: the task's nrows (<= NR_MAX) over RS sub-groups
+  const int base = nrows / RS, rem = nrows - base * RS;
+  const int row_off = rsub * base + min(rsub, rem);
+  const int cnt = base + (rsub < rem ? 1 : 0);
   const int Ho = 2 * f.Hin, Wo = 2 * f.Win;
   const int n = ((X0 - 1) >> 1) + c;                          // plane column; stage column = c + 1
   constexpr uint32_t kRowB = PC * 16, kGroupB = 12 * kRowB, kPlaneB = 4 * kGroupB;
@@ -139,16 +140,16 @@ __device__ __forceinline__ void fir_produce_group_smem(const FusedFirParams& f, 
   int m = m_h + row_off, r = r_h + row_off;
   // the noise of all (at most four) output rows of this lane is requested before any arithmetic: an L2 round trip per
   // row in the loop below was the top stall of the first version (ncu: long scoreboard)
-  float2 nzv[2 * (kBase + (kRem ? 1 : 0))];
+  float2 nzv[2 * kMaxCnt];
 #pragma unroll
-  for (int q = 0; q < 2 * (kBase + (kRem ? 1 : 0)); ++q) {
+  for (int q = 0; q < 2 * kMaxCnt; ++q) {
     const int Y = 2 * m + q;
     nzv[q] = make_float2(0.f, 0.f);
     if (nzx_ok && q < 2 * cnt && Y >= 0 && Y < Ho) nzv[q] = __ldg(reinterpret_cast<const float2*>(nz_base + static_cast<size_t>(Y) * Wo + Xa));
   }
   FH ho_prev = hrow(true, r - 1), he_cur = hrow(false, r), ho_cur = hrow(true, r);
 #pragma unroll
-  for (int it = 0; it < kBase + (kRem ? 1 : 0); ++it, ++m, ++r) {
+  for (int it = 0; it < kMaxCnt; ++it, ++m, ++r) {
     if (it >= cnt) break;
     const FH he_next = hrow(false, r + 1), ho_next = hrow(true, r + 1);
 #pragma unroll

@@ -25,7 +25,12 @@
 namespace sgr {
 
 constexpr int kFirRows = 12;      // plane rows m_first-1 .. m_first+10 feed the 18 halo-tile rows (fir_producer.cuh)
-constexpr int kFirWarps = 8;      // fused mode: warps 8..15 build the A halo tiles from the parity planes
+#ifndef SGR_FIR_WARPS
+#define SGR_FIR_WARPS 8
+#endif
+constexpr int kFirWarps = SGR_FIR_WARPS;      // fused mode: warps 8.. build the A halo tiles from the parity planes (8 or 12)
+constexpr int kFirParts = kFirWarps / 4;      // the 10 plane rows of a tile window are cut into 2 x 5 or 4 + 3 + 3
+constexpr int kFusedThreads = 256 + 32 * kFirWarps;
 
 template <int NT, int MT, bool FUSED = false>
 struct HaloCfg {
@@ -57,7 +62,7 @@ struct HaloCfg {
 };
 
 template <int NT, int MT, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                             const __grid_constant__ CUtensorMap tmap_planes,
                                                                             const ConvKernelParams p, const FusedFirParams f) {
   using Cfg = HaloCfg<NT, MT, FUSED>;
@@ -129,8 +134,11 @@ __global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(cons
   if (FUSED && warp >= 8) {
     // ------------------------------------------------------------------ FIR producers (fused mode; ksplit == 1)
     // every 32-channel block is built in two phases of 16 channels (plane stage h = phase): all eight warps work on the same
-    // stage — 4-channel group = pw >> 1, upper / lower five plane rows = pw & 1 — while TMA refills the other one
-    const int pw = warp - 8, gq = pw >> 1, rhalf = pw & 1;
+    // stage — 4-channel group = pw / kFirParts, part of the ten plane rows = pw % kFirParts — while TMA refills the other one
+    const int pw = warp - 8, gq = pw / kFirParts, part = pw % kFirParts;
+    const int row0 = kFirParts == 2 ? part * 5 : (part == 0 ? 0 : 1 + part * 3);      // 0,5 | 0,4,7
+    const int nrows = kFirParts == 2 ? 5 : (part == 0 ? 4 : 3);
+    constexpr int kNrMax = kFirParts == 2 ? 5 : 4;
     uint32_t ai = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile / p.m_tiles;
@@ -153,11 +161,11 @@ __global__ void __launch_bounds__(FUSED ? 512 : 256, 1) modconv_halo_kernel(cons
             uint8_t* dst8 = a_base + as * Cfg::kABytes + (h * 2 + (gq >> 1)) * Cfg::kChunkBytes + (gq & 1) * 8;
             const int group = kb * 8 + h * 4 + gq;
             if (p.fmt == kFmtBF16)
-              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtBF16, Cfg::kPC>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + rhalf * 5,
-                                                                             1 + rhalf * 5, dst8, Cfg::kChunkBytes * 4, lane);
+              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtBF16, Cfg::kPC, kNrMax>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + row0,
+                                                                                     1 + row0, nrows, dst8, Cfg::kChunkBytes * 4, lane);
             else
-              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtFP16, Cfg::kPC>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + rhalf * 5,
-                                                                             1 + rhalf * 5, dst8, Cfg::kChunkBytes * 4, lane);
+              fir_produce_group_smem<Cfg::kHW, Cfg::kHH, kFmtFP16, Cfg::kPC, kNrMax>(f, fir_sc, b, group, Y0, X0, stage, gq, m_first + row0,
+                                                                                     1 + row0, nrows, dst8, Cfg::kChunkBytes * 4, lane);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_empty[h]);
@@ -392,7 +400,7 @@ static int launch_halo_impl(const ConvKernelParams& p, const CUtensorMap& tmap, 
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   CUtensorMap tmap_planes = tmap;            // not fused: unused placeholder
   if (FUSED && make_plane_tensor_map(&tmap_planes, f.t, p.B, f.C, f.Hin + 1, f.Win + 1, Cfg::kPC)) return 1;
-  modconv_halo_kernel<NT, MT, FUSED><<<std::min(total, sms), FUSED ? 512 : 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_planes, p, f);
+  modconv_halo_kernel<NT, MT, FUSED><<<std::min(total, sms), FUSED ? kFusedThreads : 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_planes, p, f);
   count_launch();
   return check_launch("modconv_halo_kernel") ? 0 : 1;
 }
