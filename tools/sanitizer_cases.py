@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import stylegan2_oracle as orc  # noqa: E402
 import stylegan_directions_face_reenactment_b200 as pkg  # noqa: E402
 
-CASES = [(256, 1, 2, False), (64, 2, 3, True), (1024, 2, 1, False)]
+CASES = [(256, 1, 2, False), (64, 2, 3, True), (1024, 2, 1, False), (256, 2, 4, False), (1024, 2, 4, False)]
 if len(sys.argv) > 1:                                   # python tools/sanitizer_cases.py 1   -> only CASES[1]
     CASES = [CASES[int(v)] for v in sys.argv[1:]]
 for size, cm, batch, train in CASES:
