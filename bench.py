@@ -12,11 +12,13 @@ with no collective, so scaling is weak.
 
   value      frames/s with dp already resident in HBM (device timed, CUDA events, max over ranks)
   e2e        same through the public API with dp in PINNED HOST memory: H2D of dp and D2H of the fp32 frames inside the
-             timed region every step
-  roofline   the tcgen05 modconv kernel: algorithmic 3x3-conv FLOPs of the launches of one step / their summed
+             timed region every step (e2e.uint8_frames: the same loop delivering uint8 HWC frames, a quarter of the bytes)
+  roofline   the tcgen05 conv kernels: algorithmic 3x3-conv FLOPs of the launches of one step / their summed
              CUDA-event durations (events recorded by libsgr around each launch on the launching stream), against the
-             measured bf16 dense peak.  fp32 parity costs 3 bf16 MMAs per product (bf16x3): issued = 3 x algorithmic
-             for plain layers and 12 x for the polyphase up-layers; both numbers are reported.
+             measured bf16 dense peak.  fp32 parity costs 3 bf16 MMAs per product (bf16x3): issued = 3 x algorithmic.
+             In the default mode the convolutions that follow an up layer also apply that layer's FIR pass in producer
+             warps; roofline.separate_fir_pass holds the same measurement with that pass as its own HBM-bound kernel
+             (child process, SGR_FUSE_FIR=0), roofline.step_algorithmic_tflops the whole-step figure.
   cpu_baseline  the oracle port (oracle/stylegan2_oracle.py, torch-CPU) on the host cores, bounded sample.
 `--impl reference` times that same CPU implementation as the reference arm (the reference itself is Python and does
 not travel to the GPU box; its generator arithmetic is the torch-CPU conv the oracle calls).
