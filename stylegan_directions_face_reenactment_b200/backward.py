@@ -70,6 +70,8 @@ def synthesis_backward(g, lat, feats, noise, grad_image, want_param_grads=False)
             nscratch = N.lib().sgr_synthesis_wgrad_scratch_bytes(C.byref(desc.struct), batch)
             wscratch = g._workspace.get((batch, dev.index, 'wgrad'))
             if wscratch is None or wscratch.numel() < nscratch:
+                for k in [k for k in g._workspace if k[2] == 'wgrad']:      # one live scratch (as for the workspaces)
+                    del g._workspace[k]
                 wscratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
                 g._workspace[(batch, dev.index, 'wgrad')] = wscratch
             ex.params, ex.wgrad_scratch, ex.wgrad_scratch_bytes = C.pointer(pg), wscratch.data_ptr(), nscratch
