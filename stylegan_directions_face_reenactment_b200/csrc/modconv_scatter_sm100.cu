@@ -215,9 +215,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const int c = ci * 32;
           const int plane = c / CT;
           const int o0 = n_tile * CT + (c % CT);
-          // experiment 4: every tile stores to the place of sample 0's first tile (same instructions, L2-resident lines)
-          const size_t be = (p.debug & 4) ? 0 : b, ye = (p.debug & 4) ? yy : y, xe = (p.debug & 4) ? xx : x;
-          float* tptr = p.t_out + ((be * 4 + plane) * (p.cout >> 2) + (o0 >> 2)) * group_stride + (ye * p.W + xe) * 4;
+          float* tptr = p.t_out + ((static_cast<size_t>(b) * 4 + plane) * (p.cout >> 2) + (o0 >> 2)) * group_stride +
+                        (static_cast<size_t>(y) * p.W + x) * 4;
           const float* vv = v[ci & 1];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
