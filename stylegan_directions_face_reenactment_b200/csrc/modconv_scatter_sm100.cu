@@ -17,6 +17,8 @@
 // Warp roles as in modconv_sm100.cu.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "sgr_internal.h"
 #include "sgr_ptx.cuh"
 
@@ -29,7 +31,8 @@ struct ScatterCfg {
   static constexpr int kGroups = (144 * 1024) / kGroupBytes;             // 2 (NT=256), 4 (NT=128)
   static constexpr int kBSlabs = kGroups * 4;
   static constexpr int kAStages = 4;                                      // one slot per shift: slot index == shift
-  static constexpr int kSmemBytes = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
+  static constexpr int kStageOff = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
+  static constexpr int kSmemBytes = kStageOff + 8 * kTileM * 16;          // + epilogue staging: 8 channel groups x 128 pixels x 16 B
   static_assert(kSmemBytes <= 227 * 1024, "shared memory");
   static_assert(kBSlabs <= 16, "barrier block");
 };
@@ -41,6 +44,7 @@ __device__ __forceinline__ int scatter_prefix(int nt, int sft) {                
 
 template <int NT>
 __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                const __grid_constant__ CUtensorMap tmap_out,
                                                                 const ConvKernelParams p) {
   using Cfg = ScatterCfg<NT>;
   constexpr int AS = Cfg::kAStages, BSL = Cfg::kBSlabs;
@@ -211,6 +215,33 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
         // t[b][plane][cout/4][H+1][W+1][4] (fp32): a lane (pixel) stores 16 B per 4-channel group, consecutive lanes are
         // consecutive pixels -> every store instruction writes whole 32 B sectors (a [..][8] layout with 32 B per pixel
         // and two half-sector stores per lane ran the epilogue at half the L2 write rate and stalled the MMA pipe)
+        if (p.tma_store) {
+          // 32 columns = 8 channel groups of one parity plane: staged as the dense box [group][y][x][4] and stored by ONE TMA
+          // tensor store (clipped at the grid edge) — 64 STG.128 per lane and tile saturate the SM -> L2 store path (the same
+          // stores to L2-resident lines are no faster), a bulk store of the staged tile is cheaper
+          uint8_t* stg = smem + Cfg::kStageOff;
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // previous box read out of the staging
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (r < p.rows) {
+            const float* vv = v[ci & 1];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stg + (q * p.rows + r) * 16) = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (r == 0) {
+            const int c = ci * 32;
+            const int plane = c / CT;
+            const int g0 = (n_tile * CT + (c % CT)) >> 2;
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stg)), "r"(tx * p.bw * 4), "r"(ty * p.bh), "r"(g0),
+                         "r"(plane), "r"(tb)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          continue;
+        }
         if (valid && !(p.debug & 1)) {
           const int c = ci * 32;
           const int plane = c / CT;
@@ -228,6 +259,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     }
   }
 
+  if (p.tma_store && warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -250,7 +282,13 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
-  upconv_scatter_kernel<NT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, p);
+  // TMA-store epilogue: one sample per tile (the layers of 16x16 and larger), whole 32-column chunks of one plane
+  static const bool tma_off = [] { const char* e = getenv("SGR_TMA_STORE"); return e && e[0] == '0'; }();
+  ConvKernelParams q = p;
+  CUtensorMap tmap_out = tmap;
+  q.tma_store = (!tma_off && p.bb == 1 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;
+  if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.bw, p.bh, 8, 1)) return 1;
+  upconv_scatter_kernel<NT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
   count_launch();
   return check_launch("upconv_scatter_kernel") ? 0 : 1;
 }

@@ -304,7 +304,8 @@ int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int chann
   return 0;
 }
 
-int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int channels, int hp, int wp, int cols) {
+int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int channels, int hp, int wp, int cols, int rows,
+                          int box_groups, int box_planes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -314,7 +315,8 @@ int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int ch
   const cuuint64_t groups = channels / 4;
   const cuuint64_t dims[5] = {static_cast<cuuint64_t>(wp) * 4, static_cast<cuuint64_t>(hp), groups, 4, static_cast<cuuint64_t>(batch)};
   const cuuint64_t strides[4] = {static_cast<cuuint64_t>(wp) * 16, group_bytes, group_bytes * groups, group_bytes * groups * 4};
-  const cuuint32_t box[5] = {static_cast<cuuint32_t>(cols * 4), 12, 4, 4, 1};
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(cols * 4), static_cast<cuuint32_t>(rows), static_cast<cuuint32_t>(box_groups),
+                             static_cast<cuuint32_t>(box_planes), 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

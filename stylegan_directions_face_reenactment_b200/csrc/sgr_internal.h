@@ -77,6 +77,7 @@ struct ConvKernelParams {
   int nt;
   float* kpart;
   float acc_base, acc_mmas;     // acc_scale = acc_base * (1 + 1.16e-8 * acc_mmas / ksplit)
+  int tma_store;                // scatter up-conv: the epilogue stages 32 columns in shared memory and stores them with one TMA box
 };
 
 // FIR pass of the preceding scatter up-conv folded into a halo convolution's producer warps (fir_producer.cuh)
@@ -101,8 +102,10 @@ int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, c
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
                         int bb, int planes = 2, int chunk_box = kBlockK / 8);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
-// 5-D map over fp32 parity planes [B][4][C/4][Hp][Wp][4]: box = (cols x 4 floats, 12 rows, 4 groups, 4 planes, 1 sample)
-int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int channels, int hp, int wp, int cols);
+// 5-D map over fp32 parity planes [B][4][C/4][Hp][Wp][4]: box = (cols x 4 floats, rows, groups of 4 channels, planes, 1 sample);
+// the defaults are the window the fused FIR producers load, the scatter GEMM stores (cols x rows, 8 groups, 1 plane) boxes
+int make_plane_tensor_map(CUtensorMap* map, const float* base, int batch, int channels, int hp, int wp, int cols,
+                          int rows = 12, int groups = 4, int planes = 4);
 int num_sms();
 // modconv_scatter_sm100.cu: scatter-form upsampling convolution (parity planes -> p.t_out)
 int launch_upconv_scatter(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
