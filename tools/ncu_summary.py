@@ -19,7 +19,11 @@ def launches(src, dst, cmd_note='', what='python bench.py --steps 2 --warmup 3 -
     hdr = rows[0]
     ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
     agg = collections.OrderedDict()
-    for r in rows[1:]:
+    body = rows[1:]
+    if 'Process ID' in hdr and body:           # bench.py re-runs itself once with SGR_FUSE_FIR=0: keep the parent process only
+        pi = hdr.index('Process ID')
+        body = [r for r in body if r[pi] == body[0][pi]]
+    for r in body:
         name = r[ki]
         t = float(r[vi].replace(',', '')) / 1000.0            # ns -> us
         n, tot = agg.get(name, (0, 0.0))
