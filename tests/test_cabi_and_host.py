@@ -42,7 +42,9 @@ def test_library_exports_every_declared_symbol(native):
 def test_ctypes_structs_match_c_layout(native, tmp_path):
     src = tmp_path / 'layout.c'
     fields = {'sgr_conv_args': native.ConvArgs, 'sgr_styled_layer': native.StyledLayer, 'sgr_rgb_layer': native.RgbLayer,
-              'sgr_synthesis': native.Synthesis}
+              'sgr_synthesis': native.Synthesis, 'sgr_backward_extras': native.BackwardExtras,
+              'sgr_wgrad_args': native.WgradArgs, 'sgr_styled_param_grads': native.StyledParamGrads,
+              'sgr_rgb_param_grads': native.RgbParamGrads, 'sgr_param_grads': native.ParamGrads}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sgr.h"', 'int main(void){']
     for cname, ct in fields.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -71,6 +73,11 @@ def test_compute_entry_points_fail_loudly_without_gpu(native):
     s = native.Synthesis()
     assert lib.sgr_synthesis_forward(C.byref(s), None, 1, None, None, 0, None, None) != 0
     assert lib.sgr_synthesis_backward(C.byref(s), None, 1, None, None, None, None, 0, None) != 0
+    w = native.WgradArgs()
+    assert lib.sgr_modconv_wgrad(C.byref(w), None) != 0
+    assert b'no CUDA device' in lib.sgr_last_error()
+    assert lib.sgr_synthesis_backward_ex(C.byref(s), None, 1, None, None, None, None, 0, None, None) != 0
+    assert lib.sgr_wgrad_scratch_bytes(64, 64) >= 9 * 64 * 64 * 4          # at least one slice per tap
     assert lib.sgr_packed_weight_bytes(512, 512, 3, 0, 0) == 512 * 512 * 9 * 4
     assert lib.sgr_packed_weight_bytes(64, 128, 3, 1, 0) == 4 * 64 * 128 * 9 * 4
 
