@@ -19,9 +19,16 @@ with no collective, so scaling is weak.
              In the default mode the convolutions that follow an up layer also apply that layer's FIR pass in producer
              warps; roofline.separate_fir_pass holds the same measurement with that pass as its own HBM-bound kernel
              (child process, SGR_FUSE_FIR=0), roofline.step_algorithmic_tflops the whole-step figure.
-  cpu_baseline  the oracle port (oracle/stylegan2_oracle.py, torch-CPU) on the host cores, bounded sample.
-`--impl reference` times that same CPU implementation as the reference arm (the reference itself is Python and does
-not travel to the GPU box; its generator arithmetic is the torch-CPU conv the oracle calls).
+  cpu_baseline  the UNMODIFIED reference generator (baseline/_ref, copied from the reference tree by
+             tools/make_baseline_ref.py; its CUDA-only fused_leaky_relu restated for CPU tensors) on the host cores, bounded
+             sample; falls back to the oracle port (kind "port") when baseline/_ref is absent.
+  gpu_reference  the same unmodified reference on the GPU (cuDNN grouped convs + its own two JIT CUDA ops): the kernel to beat.
+  sustained  the same resident loop over >= 200 steps (the K the driver passes times 66 ms only).
+  strong_scaling  configs[2] as SURVEY 8d states it: 512 driving frames in total, batches of 32 dealt round-robin to the ranks.
+  train_step  configs[3]: A-matrix training step at B=16 per GPU (2 no-grad forwards from Z, shifted forward, the three surrogate
+             loss heads of loss_heads.py, backward to A, ONE flat NCCL all-reduce of A's 65 536-float gradient, Adam).
+`--impl reference` times the reference's own CPU implementation of the path (same unmodified reference, all host threads,
+B=32 per step) as the reference arm.
 """
 import argparse
 import ctypes
@@ -138,6 +145,53 @@ def build_problem(device, rank):
     return pkg, sd, G, A, trunc, wsrc, dp_host
 
 
+def load_reference_cpu():
+    """(Generator class, DirectionMatrix class, generate_image) of the unmodified reference in baseline/_ref, runnable on CPU
+    tensors: the one CUDA-only op (fused_leaky_relu, op/fused_act.py:53-55) gets the torch restatement of
+    op/fused_bias_act_kernel.cu:24-47 for CPU inputs.  None when baseline/_ref does not exist."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import gpu_reference_bench as grb
+        refm, RefA, ref_generate_image = grb.import_reference()
+    except Exception:
+        return None
+    import torch.nn.functional as F
+    import libs.gan.StyleGAN2.op.fused_act as fa
+
+    def flr(x, b, negative_slope=0.2, scale=2 ** 0.5):
+        return F.leaky_relu(x + b.view(1, -1, *([1] * (x.ndim - 2))), negative_slope) * scale
+    fa.fused_leaky_relu = flr
+    refm.fused_leaky_relu = flr
+    fa.FusedLeakyReLU.forward = lambda self, x: flr(x, self.bias, self.negative_slope, self.scale)
+    return refm, RefA, ref_generate_image
+
+
+def reference_cpu_problem(sd, batch):
+    """The bench workload on the reference's own classes (CPU): returns step(i) or None."""
+    import torch
+    from oracle import stylegan2_oracle as orc
+    ref = load_reference_cpu()
+    if ref is None:
+        return None
+    refm, RefA, ref_generate_image = ref
+    G = refm.Generator(SIZE, 512, 8, channel_multiplier=CM)
+    G.load_state_dict(sd, strict=True)
+    G.eval()
+    torch.manual_seed(5)
+    A = RefA(512, input_dim=15, out_dim=512, w_plus=True, num_layers=8)
+    torch.manual_seed(7)
+    trunc = G.mean_latent(4096).detach()
+    wsrc = orc.seeded_wplus(sd, 1, G.n_latent, seed=11).repeat(batch, 1, 1)
+    g = torch.Generator().manual_seed(4321)
+    dps = [torch.rand(batch, 15, generator=g) * 6 - 3 for _ in range(4)]
+
+    def step(i):
+        with torch.no_grad():
+            return ref_generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dps[i % 4]),
+                                      input_is_latent=True)
+    return step
+
+
 def cpu_generator_fps(sd, batch, repeats, threads):
     """Oracle port on the host cores: frames/s of generate_image at `batch` (bounded sample)."""
     import torch
@@ -159,7 +213,8 @@ def cpu_generator_fps(sd, batch, repeats, threads):
 
 
 def run_reference(args, rank):
-    """Reference arm: the path's CPU implementation (oracle port) on all host threads, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation of the path (unmodified generator from baseline/_ref; the oracle
+    port when that copy is absent) on all host threads, B=32 frames per step."""
     if rank != 0:
         return
     import torch
@@ -167,35 +222,121 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = orc.seeded_state_dict(SIZE, CM, seed=0)
-    sample = 4
-    n_latent = orc.synthesis_config(SIZE, CM)[3]
-    w = orc.seeded_wplus(sd, 1, n_latent, seed=11).repeat(sample, 1, 1)
-    trunc = w[:1, 0]
-    g = torch.Generator().manual_seed(4321)
-    aw = 0.03 * torch.randn(4096, 15, generator=g)
-    ab = torch.zeros(4096)
+    sample = BATCH
+    step = reference_cpu_problem(sd, sample)
+    kind = 'reference'
+    if step is None:
+        kind = 'port'
+        n_latent = orc.synthesis_config(SIZE, CM)[3]
+        w = orc.seeded_wplus(sd, 1, n_latent, seed=11).repeat(sample, 1, 1)
+        trunc = w[:1, 0]
+        g = torch.Generator().manual_seed(4321)
+        aw = 0.03 * torch.randn(4096, 15, generator=g)
+        ab = torch.zeros(4096)
 
-    def step():
-        dp = torch.rand(sample, 15, generator=g) * 6 - 3
-        shift = orc.direction_matrix_forward(aw, ab, dp, 512, 8)
-        orc.generate_image(sd, w, 0.7, trunc, SIZE, CM, shift_code=shift)
+        def step(i):
+            dp = torch.rand(sample, 15, generator=g) * 6 - 3
+            shift = orc.direction_matrix_forward(aw, ab, dp, 512, 8)
+            with torch.no_grad():
+                orc.generate_image(sd, w, 0.7, trunc, SIZE, CM, shift_code=shift)
 
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step()
-        dt = time.perf_counter() - t0
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
+    what = ('unmodified reference generator (baseline/_ref), torch-CPU' if kind == 'reference'
+            else 'torch-CPU oracle port of the reference generator')
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'sample': '%d frames per step of the same workload' % sample},
-            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d steps x %d frames, torch-CPU oracle port of the reference generator' % (args.steps, sample)},
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'size': SIZE, 'channel_multiplier': CM,
+                       'sample': '%d frames per step (the full batch of the workload), on the host CPU' % sample},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
+                             'sample': '%d steps x %d frames, %s' % (args.steps, sample, what)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+def train_step_leg(pkg, G, trunc, device, rank, world, batch=16, steps=8, warm=3):
+    """BASELINE configs[3] / SURVEY 8d cfg 4: the A-matrix training step of libs/trainer.py:150-189 at B=16 per GPU.
+    Per step: 2 no-grad forwards from Z (source / target), A(dp), the shifted forward, the three surrogate loss heads
+    (loss_heads.py: ArcFace IR-SE-50, AlexNet-LPIPS, ResNet50 regressor — random-init, batched, channels-last, bf16), backward
+    to A through sgr_synthesis_backward, ONE flat all-reduce of A's 65 536-float gradient, Adam (weight_decay 5e-4).  Also timed:
+    the same step with an L1 stand-in for the heads (generator part alone) and the all-reduce by itself."""
+    import torch
+    import torch.distributed as dist
+    from stylegan_directions_face_reenactment_b200 import dist as sdist
+    from stylegan_directions_face_reenactment_b200.loss_heads import SurrogateLossHeads
+    torch.manual_seed(5)
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=8).to(device)
+    sdist.broadcast_params_(A)
+    opt = torch.optim.Adam(A.parameters(), lr=1e-4, weight_decay=5e-4)
+    heads = SurrogateLossHeads().prepare(device)
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+
+    def step(use_heads):
+        z_src = torch.randn(batch, 512, device=device, generator=g)
+        z_tgt = torch.randn(batch, 512, device=device, generator=g)
+        with torch.no_grad():
+            src, w_src = pkg.generate_image(G, z_src, 0.7, trunc, input_is_latent=False, return_latents=True)
+            tgt = pkg.generate_image(G, z_tgt, 0.7, trunc, input_is_latent=False)
+        dp = torch.rand(batch, 15, device=device, generator=g) * 6 - 3
+        if use_heads:
+            loss_fn = lambda img: heads(img, src, tgt)[0]                  # noqa: E731
+        else:
+            loss_fn = lambda img: (img - tgt).abs().mean()                # noqa: E731
+        return sdist.train_step(G, A, opt, w_src, dp, 0.7, trunc, loss_fn)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / n], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    res = {}
+    for name, use_heads in (('full', True), ('generator_only', False)):
+        for _ in range(warm):
+            step(use_heads)
+        ms, (loss, nbytes) = timed(lambda: step(use_heads), steps)
+        res[name] = {'ms_per_step': ms, 'samples_per_s': batch * world / (ms * 1e-3), 'loss': float(loss)}
+    ar_us = 0.0
+    if world > 1:
+        flat = torch.zeros(65536, device=device)
+        for _ in range(5):
+            dist.all_reduce(flat)
+        ms, _ = timed(lambda: dist.all_reduce(flat), 50)
+        ar_us = ms * 1e3
+    w = A.linear.weight.detach().clone()
+    same = True
+    if world > 1:
+        w0 = w.clone()
+        dist.broadcast(w0, src=0)
+        same = bool(torch.equal(w, w0))
+        flag = torch.tensor([1.0 if same else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() > 0.5)
+    return {'config': 'configs[3]: A-matrix train step, 256^2 cm=1, B=%d per GPU, surrogate id + LPIPS + shape heads' % batch,
+            'n_gpus': world, 'batch_per_gpu': batch, 'steps': steps,
+            'ms_per_step': res['full']['ms_per_step'], 'samples_per_s': res['full']['samples_per_s'],
+            'generator_only': res['generator_only'],
+            'generator_share_of_step': res['generator_only']['ms_per_step'] / res['full']['ms_per_step'],
+            'allreduce_bytes': int(nbytes) if world > 1 else 65536 * 4, 'allreduce_us': ar_us,
+            'collective': 'one flat fp32 all-reduce (NCCL) of A.linear.{weight,bias}.grad per step' if world > 1 else 'none (1 rank)',
+            'replicas_identical': same, 'loss': res['full']['loss'], 'scaling': 'weak'}
 
 
 def main():
@@ -205,12 +346,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-baseline', type=int, default=1)
+    ap.add_argument('--gpu-reference', type=int, default=1)
+    ap.add_argument('--train', type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        args.steps = min(args.steps, 8)
+        args.steps = min(args.steps, 6)                          # ~3 s per 32-frame step on the box's host cores
         args.warmup = min(args.warmup, 1)
         run_reference(args, rank)
         return
@@ -303,9 +446,8 @@ def main():
     def step_e2e_u8(i):
         with torch.no_grad():
             dp = dp_host[i % len(dp_host)].to(device, non_blocking=True)
-            img = pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
-                                     input_is_latent=True)
-            u8 = pkg.frames_to_uint8(img)
+            u8 = pkg.generate_frames_uint8(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
+                                           input_is_latent=True)
         ready = torch.cuda.Event()
         ready.record()
         slot = i % 2
@@ -319,6 +461,39 @@ def main():
         step_e2e_u8(i)
     ms_e2e_u8 = timed(step_e2e_u8, args.steps, finish_e2e)
     clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed regions
+
+    # ---- sustained: the resident loop over >= 200 steps (>= 0.6 s of back-to-back launches; power-cap regime)
+    sus_steps = max(200, args.steps)
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
+    ms_sus = timed(step_resident, sus_steps)
+    sustained = {'steps': sus_steps, 'ms_per_step': ms_sus / sus_steps, 'value': BATCH * world * sus_steps / (ms_sus * 1e-3),
+                 'unit': 'frames/s', 'clocks': sampler2.stop() if rank == 0 else None}
+
+    # ---- strong scaling (SURVEY 8d cfg 3): 512 driving frames in total, batches of 32 dealt round-robin to the ranks
+    total_frames = 512
+    n_batches = total_frames // BATCH
+    mine = list(range(rank, n_batches, world))
+    g2 = torch.Generator().manual_seed(999)
+    all_dp = [(torch.rand(BATCH, 15, generator=g2) * 6 - 3) for _ in range(n_batches)]
+    my_dp = [all_dp[i].to(device) for i in mine]
+
+    def strong_pass(_i):
+        with torch.no_grad():
+            for dpb in my_dp:
+                pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dpb), input_is_latent=True)
+
+    strong_reps = 5
+    ms_strong = timed(strong_pass, strong_reps) / strong_reps
+    strong = {'frames_total': total_frames, 'batch': BATCH, 'batches_per_rank_max': len(range(0, n_batches, world)),
+              'ms': ms_strong, 'value': total_frames / (ms_strong * 1e-3), 'unit': 'frames/s', 'scaling': 'strong',
+              'note': 'frames/s = 512 / wall (max over ranks, CUDA events, mean of %d passes after the warm-up of the weak leg); the '
+                      'limiter at large N is the quantisation to whole 32-frame batches per rank (2 at N=8) plus one launch chain per '
+                      'batch, no collective is involved' % strong_reps}
+
+    # ---- configs[3]: A-matrix train step, B=16 per GPU, surrogate loss heads, all-reduce of A's gradient
+    train = train_step_leg(pkg, G, trunc, device, rank, world) if args.train else None
 
     # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch)
     roofline, layers = None, None
@@ -363,6 +538,10 @@ def main():
                     'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
                     'traffic': ncu_traffic_bytes(),
                     'issued_tflops': issued, 'issued_frac': issued / pk['bf16'], 'peak_source': pk['src'],
+                    'peak_burst': pk['bf16_burst'], 'frac_vs_burst': achieved / pk['bf16_burst'],
+                    'issued_frac_vs_burst': issued / pk['bf16_burst'],
+                    'peak_note': 'frac / issued_frac are against the SUSTAINED cuBLAS bf16 figure of MEASURED_PEAKS.json (the timed '
+                                 'region sits inside a long run of back-to-back steps: see `sustained`); *_vs_burst against the burst figure',
                     'note': 'achieved = algorithmic conv FLOPs (SURVEY 8d, 29.746 GFLOP/frame) / summed CUDA-event time of '
                             'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
                             'comparable to the bf16 dense peak',
@@ -403,9 +582,36 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_baseline:
         threads = os.cpu_count() or 1
-        fps = cpu_generator_fps(sd, 4, 2, threads)
-        cpu_baseline = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                        'sample': 'best of 2 x 4 frames after 1 warm-up, torch-CPU oracle port (generate_image, 256^2 cm=1)'}
+        torch.set_num_threads(threads)
+        ref_step = reference_cpu_problem(sd, 8)
+        if ref_step is not None:
+            best = None
+            for i in range(3):
+                t0 = time.perf_counter()
+                ref_step(i)
+                dt = time.perf_counter() - t0
+                if i > 0:
+                    best = dt if best is None else min(best, dt)
+            cpu_baseline = {'value': 8 / best, 'unit': 'frames/s', 'cores': threads, 'kind': 'reference',
+                            'sample': 'best of 2 x 8 frames after 1 warm-up: unmodified reference generator (baseline/_ref, '
+                                      'generate_image, 256^2 cm=1) on the host CPU, fused_leaky_relu restated for CPU tensors'}
+        else:
+            fps = cpu_generator_fps(sd, 4, 2, threads)
+            cpu_baseline = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                            'sample': 'best of 2 x 4 frames after 1 warm-up, torch-CPU oracle port (generate_image, 256^2 cm=1)'}
+
+    # ---- the unmodified reference on this GPU (cuDNN grouped convs + its JIT ops): child process, its own CUDA context
+    gpu_reference = None
+    if rank == 0 and world == 1 and args.gpu_reference and not os.environ.get('SGR_BENCH_CHILD'):
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'gpu_reference_bench.py'), '--steps', '20',
+                                  '--warmup', '3'], capture_output=True, text=True, timeout=600)
+            gpu_reference = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001  (informational leg only)
+            gpu_reference = {'unavailable': str(e)[:200]}
+        if gpu_reference and 'fp32' in gpu_reference:
+            gpu_reference['speedup_vs_reference_fp32'] = value / gpu_reference['fp32']['frames_s']
+            gpu_reference['speedup_vs_reference_tf32_default'] = value / gpu_reference['tf32']['frames_s']
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
@@ -418,8 +624,9 @@ def main():
                         'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE * 4, 'ms_per_step': ms_e2e / args.steps,
                         'uint8_frames': {'value': frames / (ms_e2e_u8 * 1e-3), 'unit': 'frames/s',
                                          'd2h_bytes_per_step': BATCH * 3 * SIZE * SIZE,
-                                         'note': 'same loop with the fused uint8 HWC output stage (sgr_frames_to_uint8)'}},
+                                         'note': 'same loop, uint8 HWC frames written by the last ToRGB tail (sgr_synthesis_forward_ex: clamp / scale / uint8 fused, no fp32 frame)'}},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+                'gpu_reference': gpu_reference, 'sustained': sustained, 'strong_scaling': strong, 'train_step': train,
                 'layers': layers}
         print(json.dumps(line), flush=True)
     if world > 1:

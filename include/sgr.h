@@ -225,6 +225,18 @@ size_t sgr_synthesis_workspace_bytes(const sgr_synthesis* net, int batch);
 int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
                           size_t workspace_bytes, float* const* feats, void* stream);
 
+/* Same, with the output stage of the callers folded into the last ToRGB tail: `frames_u8`
+ * [B,u8_h,u8_w,3] receives uint8 HWC frames computed as libs/utilities/generic.py:146-148 (AdaptiveAvgPool2d when
+ * u8_h < size; u8_h, u8_w must divide size), libs/utilities/image_utils.py:97-111 (tensor_to_image: clamp to [-1,1],
+ * (v+1)/(2+1e-5)*255) and np.uint8 (libs/utilities/utils_inference.py:16) produce them.  `image` may then be NULL: the fp32
+ * frame is never written. */
+typedef struct sgr_forward_extras {
+  unsigned char* frames_u8;
+  int u8_h, u8_w;
+} sgr_forward_extras;
+int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
+                             size_t workspace_bytes, float* const* feats, const sgr_forward_extras* extras, void* stream);
+
 /* Gradient of sum(image * grad_image) with respect to `latent` (dlatent: [B,n_latent,512], overwritten).
  * feats: the n_styled saved StyledConv outputs of the forward call (all required).  Replaces ATen autograd through
  * F.conv2d / F.conv_transpose2d and the modulation graph (model.py:232-273) for the A-matrix training step

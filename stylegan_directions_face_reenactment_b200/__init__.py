@@ -12,9 +12,9 @@ from .direction_matrix import DirectionMatrix
 from .model import (Blur, ConstantInput, EqualLinear, Generator, ModulatedConv2d, NoiseInjection, PixelNorm, StyledConv,
                     ToRGB, Upsample, make_kernel)
 from .ops import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
-from .reenact import frames_to_uint8, generate_image, get_shifted_latent_code
+from .reenact import frames_to_uint8, generate_frames_uint8, generate_image, get_shifted_latent_code
 from . import formats  # noqa: F401  (on-disk formats: generator / A-matrix checkpoints, latent-code .npy files)
 
-__all__ = ['Generator', 'DirectionMatrix', 'generate_image', 'get_shifted_latent_code', 'frames_to_uint8', 'upfirdn2d',
+__all__ = ['Generator', 'DirectionMatrix', 'generate_image', 'get_shifted_latent_code', 'frames_to_uint8', 'generate_frames_uint8', 'upfirdn2d',
            'fused_leaky_relu', 'FusedLeakyReLU', 'EqualLinear', 'ModulatedConv2d', 'StyledConv', 'ToRGB', 'Upsample',
            'Blur', 'ConstantInput', 'NoiseInjection', 'PixelNorm', 'make_kernel']

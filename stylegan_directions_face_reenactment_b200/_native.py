@@ -68,6 +68,10 @@ class BackwardExtras(C.Structure):
                 ('params', C.POINTER(ParamGrads)), ('wgrad_scratch', _fp), ('wgrad_scratch_bytes', C.c_size_t)]
 
 
+class ForwardExtras(C.Structure):
+    _fields_ = [('frames_u8', _fp), ('u8_h', C.c_int), ('u8_w', C.c_int)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [('batch', C.c_int), ('cin', C.c_int), ('cout', C.c_int), ('h_in', C.c_int), ('w_in', C.c_int),
                 ('up', C.c_int), ('x_c8', _fp), ('gz_c8', _fp), ('gw', _fp), ('scratch', _fp), ('scratch_bytes', C.c_size_t)]
@@ -110,6 +114,8 @@ SIGNATURES = {
                                             C.POINTER(BackwardExtras), _fp]),
     'sgr_synthesis_forward': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, _fp, _fp, C.c_size_t, C.POINTER(_fp),
                                         _fp]),
+    'sgr_synthesis_forward_ex': (C.c_int, [C.POINTER(Synthesis), _fp, C.c_int, _fp, _fp, C.c_size_t, C.POINTER(_fp),
+                                           C.POINTER(ForwardExtras), _fp]),
 }
 
 _lib = None

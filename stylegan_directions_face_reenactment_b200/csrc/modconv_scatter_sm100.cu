@@ -31,6 +31,8 @@ struct ScatterCfg {
   static constexpr int kGroups = (144 * 1024) / kGroupBytes;             // 2 (NT=256), 4 (NT=128)
   static constexpr int kBSlabs = kGroups * 4;
   static constexpr int kAStages = 4;                                      // one slot per shift: slot index == shift
+  static constexpr int kHaloStages = 3;                                   // wrapped-halo tiles: ring of channel blocks in the same 64 KiB
+  static constexpr int kHaloStageBytes = 21760;                           // >= 8 chunk-planes x (129 + 32) entries x 16 B, 128-aligned
   static constexpr int kStageOff = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
   static constexpr int kSmemBytes = kStageOff + 8 * kTileM * 16;          // + epilogue staging: 8 channel groups x 128 pixels x 16 B
   static_assert(kSmemBytes <= 227 * 1024, "shared memory");
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * (p.single ? 64u : 128u);   // single pass: hi plane only
+      const uint32_t halo_bytes = static_cast<uint32_t>(p.bw * (p.bh + 1)) * (p.single ? 64u : 128u);
       const uint32_t b_row = p.single ? 64u : 128u;                                       // slabs are plane-major: hi half first
       uint32_t g = 0;                                  // running channel-block counter: ring slots and phases
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -104,19 +107,28 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
         const int ty = m % p.tiles_y;
         const int tb = m / p.tiles_y;
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+        const int hx0 = tx * (p.bw - 1), hy0 = ty * p.bh;                  // wrapped-halo tiles: bw - 1 valid columns
         const uint8_t* wkc = reinterpret_cast<const uint8_t*>(p.wpacked) +
                              static_cast<size_t>(n_tile) * p.kchunks * Cfg::kGroupBytes;
         for (int kc = 0; kc < p.kchunks; ++kc, ++g, wkc += Cfg::kGroupBytes) {
           const uint32_t grp = g % Cfg::kGroups;
           const uint32_t a_par = (g & 1) ^ 1, b_par = ((g / Cfg::kGroups) & 1) ^ 1;
           uint8_t* bdst = b_base + grp * Cfg::kGroupBytes;
+          if (p.halo) {              // one box per channel block: tile + top row / left column halo, all four shifts read it
+            const uint32_t hs = g % Cfg::kHaloStages;
+            mbar_wait(&a_empty[hs], ((g / Cfg::kHaloStages) & 1) ^ 1);
+            mbar_expect_tx(&a_full[hs], halo_bytes);
+            tma_load_5d(a_base + hs * Cfg::kHaloStageBytes, &tmap, &a_full[hs], (hx0 - 1) * 8, hy0 - 1, b0, kc * 4, 0);
+          }
 #pragma unroll
           for (int sft = 0; sft < 4; ++sft) {
             const int n_s = scatter_rows(NT, sft), prefix = scatter_prefix(NT, sft);
             const uint32_t bs = grp * 4 + sft;
-            mbar_wait(&a_empty[sft], a_par);
-            mbar_expect_tx(&a_full[sft], a_bytes);
-            tma_load_5d(a_base + sft * kABytes, &tmap, &a_full[sft], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
+            if (!p.halo) {
+              mbar_wait(&a_empty[sft], a_par);
+              mbar_expect_tx(&a_full[sft], a_bytes);
+              tma_load_5d(a_base + sft * kABytes, &tmap, &a_full[sft], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
+            }
             mbar_wait(&b_empty[bs], b_par);
             mbar_expect_tx(&b_full[bs], n_s * b_row);
             bulk_g2s(bdst + prefix * 128, wkc + prefix * 128, n_s * b_row, &b_full[bs]);
@@ -128,8 +140,10 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       // descriptors = base (LBO/SBO/version fields + ring base address) + byte offset >> 4
-      const uint32_t a_lbo = static_cast<uint32_t>(p.rows) * 16;
+      const uint32_t a_lbo = static_cast<uint32_t>(p.halo ? p.bw * (p.bh + 1) : p.rows) * 16;      // bytes per chunk-plane of a box
       const uint64_t a_desc0 = umma_desc(smem_u32(a_base), a_lbo, 128);
+      // wrapped-halo tiles: M row r of shift (a, b) = box entry bw + 1 + r - (a * bw + b)
+      const uint64_t h_off[4] = {static_cast<uint64_t>(p.bw + 1), static_cast<uint64_t>(p.bw), 1, 0};
       const uint64_t a_lo_off = (a_lbo * 4) >> 4, a_j_off = (a_lbo * 2) >> 4;
       uint64_t b_desc0[4];
       uint32_t idesc[4];
@@ -153,10 +167,12 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           for (int sft = 0; sft < 4; ++sft) {
             const uint32_t n_s = scatter_rows(NT, sft);
             const uint32_t coloff = sft >= 2 ? NT / 4 : 0;        // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
-            mbar_wait(&a_full[sft], a_par);
+            if (!p.halo) mbar_wait(&a_full[sft], a_par);
+            else if (sft == 0) mbar_wait(&a_full[g % Cfg::kHaloStages], (g / Cfg::kHaloStages) & 1);
             mbar_wait(&b_full[grp * 4 + sft], b_par);
             tc_fence_after();
-            const uint64_t a_hi0 = a_desc0 + ((sft * kABytes) >> 4);
+            const uint64_t a_hi0 = p.halo ? a_desc0 + (((g % Cfg::kHaloStages) * Cfg::kHaloStageBytes) >> 4) + h_off[sft]
+                                          : a_desc0 + ((sft * kABytes) >> 4);
             const uint64_t b_hi0 = b_desc0[sft] + grp_off;
 #pragma unroll
             for (int j = 0; j < kBlockK / 16; ++j) {
@@ -170,7 +186,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
                 umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], (kc | sft | j) != 0);
               }
             }
-            umma_commit(&a_empty[sft]);
+            if (!p.halo) umma_commit(&a_empty[sft]);
+            else if (sft == 3) umma_commit(&a_empty[g % Cfg::kHaloStages]);
             umma_commit(&b_empty[grp * 4 + sft]);
           }
         }
@@ -181,9 +198,21 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // ------------------------------------------------------------------ epilogue: raw parity planes -> HBM
     const int ew = warp - 4;
     const int r = ew * 32 + lane;
-    const int xx = r % p.bw;
-    const int yy = (r / p.bw) % p.bh;
-    const int bl = r / (p.bw * p.bh);
+    int xx = r % p.bw;
+    int yy = (r / p.bw) % p.bh;
+    int bl = r / (p.bw * p.bh);
+    int slot = r;                                      // position inside the staged / stored box; < 0: nothing to store
+    int sx = p.bw, sy = p.bh;                          // tile stride on the grid
+    if (p.halo) {                                      // box entry bw + 1 + r: column 0 of the box is halo (garbage rows)
+      const int e = p.bw + 1 + r;
+      xx = e % p.bw - 1;
+      yy = e / p.bw - 1;
+      bl = 0;
+      sx = p.bw - 1;
+      slot = (xx >= 0 && yy < p.bh) ? yy * (p.bw - 1) + xx : -1;
+    } else if (r >= p.rows) {
+      slot = -1;
+    }
     constexpr int CT = NT / 4;
     const size_t group_stride = static_cast<size_t>(p.H) * p.W * 4;
     uint32_t tcount = 0;
@@ -194,8 +223,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
       const int tb = m / p.tiles_y;
-      const int b = tb * p.bb + bl, y = ty * p.bh + yy, x = tx * p.bw + xx;
-      const bool valid = r < p.rows && b < p.B && y < p.H && x < p.W;
+      const int b = tb * p.bb + bl, y = ty * sy + yy, x = tx * sx + xx;
+      const bool valid = slot >= 0 && b < p.B && y < p.H && x < p.W;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
@@ -222,11 +251,11 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           uint8_t* stg = smem + Cfg::kStageOff;
           if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // previous box read out of the staging
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (r < p.rows) {
+          if (slot >= 0) {
             const float* vv = v[ci & 1];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(stg + (q * p.rows + r) * 16) = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
+              *reinterpret_cast<float4*>(stg + (q * p.rows + slot) * 16) = make_float4(vv[4 * q], vv[4 * q + 1], vv[4 * q + 2], vv[4 * q + 3]);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -235,7 +264,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
             const int plane = c / CT;
             const int g0 = (n_tile * CT + (c % CT)) >> 2;
             asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stg)), "r"(tx * p.bw * 4), "r"(ty * p.bh), "r"(g0),
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stg)), "r"(tx * sx * 4), "r"(ty * sy), "r"(g0),
                          "r"(plane), "r"(tb)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -287,7 +316,7 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
   ConvKernelParams q = p;
   CUtensorMap tmap_out = tmap;
   q.tma_store = (!tma_off && p.bb == 1 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;
-  if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.bw, p.bh, 8, 1)) return 1;
+  if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
   upconv_scatter_kernel<NT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
   count_launch();
   return check_launch("upconv_scatter_kernel") ? 0 : 1;

@@ -272,8 +272,8 @@ static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* 
     if (make_act_tensor_map(&tmap, args->x_c8, args->batch, 4 * args->cin, args->h_in + 1, args->w_in + 1, p.bw, p.bh, p.bb,
                             p.single ? 1 : 2))
       return 1;
-  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh, p.bb,
-                                 p.single ? 1 : 2)) {
+  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh + (p.halo ? 1 : 0),
+                                 p.bb, p.single ? 1 : 2)) {
     return 1;
   }
   if (args->up != 2)
@@ -334,10 +334,20 @@ size_t sgr_synthesis_workspace_bytes(const sgr_synthesis* net, int batch) {
 
 int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
                           size_t workspace_bytes, float* const* feats, void* stream) {
+  return sgr_synthesis_forward_ex(net, latent, batch, image, workspace, workspace_bytes, feats, nullptr, stream);
+}
+
+int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int batch, float* image, void* workspace,
+                             size_t workspace_bytes, float* const* feats, const sgr_forward_extras* extras, void* stream) {
   if (!have_device()) return 1;
   SynthPlan pl;
   if (plan_synthesis(net, batch, &pl)) return 1;
-  if (!latent || !image || !workspace || workspace_bytes < pl.total) {
+  unsigned char* frames_u8 = extras ? extras->frames_u8 : nullptr;
+  if (frames_u8 && (extras->u8_h <= 0 || extras->u8_w <= 0 || net->size % extras->u8_h != 0 || net->size % extras->u8_w != 0)) {
+    set_error("synthesis_forward: uint8 frame size %dx%d must divide the network size %d", extras->u8_h, extras->u8_w, net->size);
+    return 1;
+  }
+  if (!latent || (!image && !frames_u8) || !workspace || workspace_bytes < pl.total) {
     set_error("synthesis_forward: workspace too small (%zu < %zu) or null pointer", workspace_bytes, pl.total);
     return 1;
   }
@@ -468,7 +478,13 @@ int sgr_synthesis_forward(const sgr_synthesis* net, const float* latent, int bat
         set_error("synthesis_forward: rgb %d needs an upsample kernel", r);
         return 1;
       }
-      if (torgb_tail_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, dst, batch, res, res, st)) return 1;
+      if (last && frames_u8 &&
+          torgb_tail_u8_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, frames_u8, batch, res, res,
+                               extras->u8_h, extras->u8_w, st))
+        return 1;
+      if ((!last || image) &&
+          torgb_tail_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, dst, batch, res, res, st))
+        return 1;
       prev_skip = dst;
       skip_cur = 1 - skip_cur;
     }

@@ -78,6 +78,9 @@ struct ConvKernelParams {
   float* kpart;
   float acc_base, acc_mmas;     // acc_scale = acc_base * (1 + 1.16e-8 * acc_mmas / ksplit)
   int tma_store;                // scatter up-conv: the epilogue stages 32 columns in shared memory and stores them with one TMA box
+  // scatter up-conv, wrapped-halo tiles (modconv_scatter_sm100.cu): ONE dense TMA box of bw x (bh + 1) pixels per channel block
+  // whose first row / column are the halo; the four shifts are descriptor offsets into it.  bw - 1 valid columns, bh valid rows.
+  int halo;
 };
 
 // FIR pass of the preceding scatter up-conv folded into a halo convolution's producer warps (fir_producer.cuh)
@@ -173,6 +176,8 @@ int bias_act_launch(const float* x, const float* bias, const float* ref, float* 
                     long long inner, int grad, float slope, float scale, cudaStream_t st);
 int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
                       float* out, int batch, int H, int W, cudaStream_t st);
+int torgb_tail_u8_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
+                         unsigned char* out, int batch, int H, int W, int out_h, int out_w, cudaStream_t st);
 int frames_to_uint8_launch(const float* x, unsigned char* y, int batch, int H, int W, int out_h, int out_w, cudaStream_t st);
 // up_finish_sm100.cu: FIR + fused epilogue over the parity planes of a scatter up-conv
 int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st);

@@ -276,6 +276,77 @@ int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const 
   return check_launch("torgb_tail_kernel") ? 0 : 1;
 }
 
+// ------------------------------------------------------------------------------------------------ ToRGB tail + output stage
+// Last level, when the caller wants bytes: the same slot sum + bias + 2x FIR skip as torgb_tail_kernel (same
+// operation order, so the frame is bit-identical to the fp32 one), then generate_image's 256-pooling (generic.py:146-148),
+// tensor_to_image's clamp / scale (image_utils.py:97-111) and np.uint8 (utils_inference.py:16) — the fp32 frame is never
+// written.  One thread per OUTPUT pixel: lanes run along x, the three channels leave as 3 adjacent bytes.
+__global__ void torgb_tail_u8_kernel(const float* __restrict__ rgb_acc, int slots, const float* __restrict__ bias,
+                                     const float* __restrict__ skip_in, const float* __restrict__ fir,
+                                     unsigned char* __restrict__ out, int batch, int H, int W, int out_h, int out_w) {
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = fir ? fir[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)] : 0.f;
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= out_w) return;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int fy = H / out_h, fx = W / out_w;
+  const int h2 = H / 2, w2 = W / 2;
+  const int planes = batch * 3;
+  const float inv_area = 1.f / static_cast<float>(fy * fx);
+  unsigned char px[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int pl = b * 3 + c;
+    const float bc = __ldg(bias + c);
+    const float* sp = skip_in ? skip_in + static_cast<size_t>(pl) * h2 * w2 : nullptr;
+    float v = 0.f;
+    for (int dy = 0; dy < fy; ++dy) {
+      const int y = oy * fy + dy;
+      for (int dx = 0; dx < fx; ++dx) {
+        const int x = ox * fx + dx;
+        float a = __ldg(rgb_acc + (static_cast<size_t>(pl) * H + y) * W + x);
+        for (int s = 1; s < slots; ++s) a += __ldg(rgb_acc + ((static_cast<size_t>(s) * planes + pl) * H + y) * W + x);
+        float acc = a + bc;
+        if (sp) {
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky) {
+            const int uy = y + ky - 2;
+            if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+            const float* row = sp + static_cast<size_t>(uy >> 1) * w2;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const int ux = x + kx - 2;
+              if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+              acc = fmaf(sk[ky * 4 + kx], __ldg(row + (ux >> 1)), acc);
+            }
+          }
+        }
+        v = (fy == 1 && fx == 1) ? acc : v + acc;
+      }
+    }
+    if (fy != 1 || fx != 1) v *= inv_area;
+    v = fminf(fmaxf(v, -1.f), 1.f);
+    v = __fdiv_rn(v + 1.f, 2.00001f) * 255.f;
+    px[c] = static_cast<unsigned char>(static_cast<int>(v));
+  }
+  unsigned char* dst = out + ((static_cast<size_t>(b) * out_h + oy) * out_w + ox) * 3;
+  dst[0] = px[0]; dst[1] = px[1]; dst[2] = px[2];
+}
+
+int torgb_tail_u8_launch(const float* rgb_acc, int slots, const float* bias, const float* skip_in, const float* fir,
+                         unsigned char* out, int batch, int H, int W, int out_h, int out_w, cudaStream_t st) {
+  if (out_h <= 0 || out_w <= 0 || H % out_h != 0 || W % out_w != 0 || out_h > 65535 || batch > 65535) {
+    set_error("torgb_tail_u8: output %dx%d must divide the frame size %dx%d", out_h, out_w, H, W);
+    return 1;
+  }
+  const int threads = out_w >= 128 ? 128 : (out_w >= 64 ? 64 : 32);
+  dim3 grid((out_w + threads - 1) / threads, out_h, batch);
+  torgb_tail_u8_kernel<<<grid, threads, 0, st>>>(rgb_acc, slots, bias, skip_in, fir, out, batch, H, W, out_h, out_w);
+  count_launch();
+  return check_launch("torgb_tail_u8_kernel") ? 0 : 1;
+}
+
 // ------------------------------------------------------------------------------------------------ output stage
 // Frames [B,3,H,W] fp32 in [-1,1] -> uint8 [B,H,W,3] exactly as the reference post-processing does on the way to the
 // video writer (libs/utilities/image_utils.py:97-111 tensor_to_image + np.uint8 at utils_inference.py:16):

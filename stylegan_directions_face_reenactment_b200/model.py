@@ -219,6 +219,22 @@ class ModulatedConv2d(nn.Module):
 def _modconv_module_forward(conv, x, style, noise, noise_weight, bias, act):
     if not x.is_cuda:
         raise RuntimeError('ModulatedConv2d: input must be a CUDA tensor (no CPU fallback)')
+    if torch.is_grad_enabled():
+        # the layer-by-layer entry points launch raw kernels: there is no autograd node behind them (Generator.forward is the
+        # differentiable path).  Never return a tensor that silently drops a gradient somebody asked for.
+        if x.requires_grad or style.requires_grad:
+            raise RuntimeError('module-level ModulatedConv2d / StyledConv / ToRGB calls are not differentiable (input or style '
+                               'requires grad): run the whole network through Generator.forward, or call under torch.no_grad()')
+        if any(p.requires_grad for p in conv.parameters()) and not conv.__dict__.get('_warned_nograd'):
+            import warnings
+            warnings.warn('module-level ModulatedConv2d / StyledConv / ToRGB calls do not record autograd history: parameter '
+                          'gradients are only available through Generator.forward', stacklevel=3)
+            conv.__dict__['_warned_nograd'] = True
+    with torch.cuda.device(x.device):
+        return _modconv_module_forward_impl(conv, x, style, noise, noise_weight, bias, act)
+
+
+def _modconv_module_forward_impl(conv, x, style, noise, noise_weight, bias, act):
     lib = N.lib()
     st = N.stream()
     x = x.contiguous().float()
@@ -407,6 +423,15 @@ class Generator(nn.Module):
 
     def rgb_layers(self):
         return [self.to_rgb1] + list(self.to_rgbs)
+
+    def synthesis_uint8(self, latent, noise=None, size=None):
+        """latent [B, n_latent, 512] -> uint8 HWC frames [B,size,size,3] (size divides self.size; default self.size): the
+        callers' output stage (256-pooling, clamp, scale, uint8; reference generic.py:146-148, image_utils.py:97-111) fused
+        into the last ToRGB tail.  No autograd."""
+        from .synthesis import synthesis_forward_u8
+        if noise is None:
+            noise = [getattr(self.noises, 'noise_%d' % i) for i in range(self.num_layers)]
+        return synthesis_forward_u8(self, latent.detach(), noise, size)
 
     def synthesis(self, latent, noise=None, return_features=False):
         """latent [B, n_latent, 512] -> image [B,3,size,size]; optionally also every StyledConv output (NCHW fp32)."""

@@ -30,8 +30,9 @@ def _upfirdn2d_raw(x, kernel, up, down, pad0, pad1):
         if y.numel():
             y.zero_()
         return y
-    N.check(N.lib().sgr_upfirdn2d(N.ptr(x), N.ptr(y), N.ptr(kernel), b * c, h, w, up, down, pad0, pad1, kh, kw,
-                                  N.stream()), 'sgr_upfirdn2d')
+    with torch.cuda.device(x.device):
+        N.check(N.lib().sgr_upfirdn2d(N.ptr(x), N.ptr(y), N.ptr(kernel), b * c, h, w, up, down, pad0, pad1, kh, kw,
+                                      N.stream()), 'sgr_upfirdn2d')
     return y
 
 
@@ -51,10 +52,16 @@ class _UpFirDn2d(torch.autograd.Function):
         kernel, = ctx.saved_tensors
         up, down, pad0, pad1, in_h, in_w, out_h, out_w = ctx.cfg
         kh, kw = kernel.shape
-        g0 = kw - pad0 - 1
-        # per-axis g_pad1 can differ by the decimation remainder; the larger one only appends outputs, sliced off below
-        g1 = max(in_w * up - out_w * down, in_h * up - out_h * down) + pad0 - up + 1
-        gx =_UpFirDn2d.apply(gy, torch.flip(kernel, [0, 1]), down, up, g0, g1)
+        # g_pad per axis as op/upfirdn2d.py:112-117: g_pad_x0 = kernel_w - pad_x0 - 1, g_pad_y0 = kernel_h - pad_y0 - 1,
+        # g_pad_x1 = in_w * up - out_w * down + pad_x0 - up + 1 (likewise y).  sgr_upfirdn2d takes ONE (pad0, pad1) pair for
+        # both axes (as the reference's Python entry point does), so the axes must agree — they do for every square FIR.
+        gx0, gy0 = kw - pad0 - 1, kh - pad0 - 1
+        gx1 = in_w * up - out_w * down + pad0 - up + 1
+        gy1 = in_h * up - out_h * down + pad0 - up + 1
+        if gx0 != gy0:
+            raise NotImplementedError('upfirdn2d backward: non-square FIR kernels (%dx%d) need per-axis padding' % (kh, kw))
+        # the trailing pads can differ by the decimation remainder: the larger one only appends outputs, sliced off below
+        gx = _UpFirDn2d.apply(gy, torch.flip(kernel, [0, 1]), down, up, gx0, max(gx1, gy1))
         return gx[:, :, :in_h, :in_w], None, None, None, None, None
 
 
@@ -76,8 +83,9 @@ def _bias_act_raw(x, bias, ref, grad, slope, scale):
         inner *= d
     if x.ndim == 1:
         outer, channels = 1, x.shape[0]
-    N.check(N.lib().sgr_fused_bias_act(N.ptr(x), N.ptr(bias), N.ptr(ref), N.ptr(y), outer, channels, inner, grad,
-                                       slope, scale, N.stream()), 'sgr_fused_bias_act')
+    with torch.cuda.device(x.device):
+        N.check(N.lib().sgr_fused_bias_act(N.ptr(x), N.ptr(bias), N.ptr(ref), N.ptr(y), outer, channels, inner, grad,
+                                           slope, scale, N.stream()), 'sgr_fused_bias_act')
     return y
 
 

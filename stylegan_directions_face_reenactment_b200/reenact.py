@@ -37,6 +37,26 @@ def generate_image(G, latent_code, truncation, trunc, w_plus=True, num_layers_sh
     return (imgs, latents) if return_latents else imgs
 
 
+def generate_frames_uint8(G, latent_code, truncation, trunc, w_plus=True, num_layers_shift=8, shift_code=None,
+                          input_is_latent=False, size=256):
+    """generate_image (generic.py:137-152) followed by the reference's frame post-processing (tensor_to_image + np.uint8,
+    image_utils.py:97-111, utils_inference.py:16) in ONE pass: uint8 HWC frames [B,h,w,3] with h = min(G.size, size), written by
+    the last ToRGB tail (G.synthesis_uint8) — a quarter of the device->host bytes and no fp32 frame in HBM.  No autograd."""
+    with torch.no_grad():
+        code = latent_code
+        if shift_code is not None:
+            code = get_shifted_latent_code(G, latent_code, shift_code, input_is_latent=input_is_latent, truncation=truncation,
+                                           truncation_latent=trunc, w_plus=w_plus, num_layers=num_layers_shift)
+            input_is_latent = True
+        if not input_is_latent:
+            code = G.get_latent(code)
+        if truncation < 1:
+            code = trunc + truncation * (code - trunc)
+        if code.ndim < 3:
+            code = code.unsqueeze(1).repeat(1, G.n_latent, 1)
+        return G.synthesis_uint8(code, size=min(G.size, size))
+
+
 def frames_to_uint8(images, size=None):
     """Fused output stage: [B,3,H,W] fp32 frames in [-1,1] -> [B,h,w,3] uint8 CUDA tensor with the
     arithmetic of the reference's tensor_to_image + np.uint8 (libs/utilities/image_utils.py:97-111,

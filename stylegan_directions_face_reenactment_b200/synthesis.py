@@ -194,6 +194,30 @@ def synthesis_forward(g, latent, noise, want_feats):
     return image, feats, lat, desc.noise_used
 
 
+def synthesis_forward_u8(g, latent, noise, size=None):
+    """No-grad forward that delivers uint8 HWC frames [B,size,size,3] straight from the last ToRGB tail
+    (sgr_synthesis_forward_ex: 256-pooling + clamp + scale + uint8 fused, the fp32 frame is never written; SURVEY.md §8f-2,
+    reference libs/utilities/generic.py:146-148, image_utils.py:97-111, utils_inference.py:16)."""
+    if not latent.is_cuda:
+        raise RuntimeError('Generator: latent must be a CUDA tensor (libsgr has no CPU fallback)')
+    if latent.ndim != 3 or latent.shape[1] != g.n_latent or latent.shape[2] != g.style_dim:
+        raise RuntimeError('latent must be [B,%d,%d], got %s' % (g.n_latent, g.style_dim, tuple(latent.shape)))
+    lat = _f32c(latent)
+    batch, dev = lat.shape[0], lat.device
+    size = g.size if size is None else int(size)
+    if size <= 0 or g.size % size:
+        raise RuntimeError('uint8 frame size %d must divide the network size %d' % (size, g.size))
+    with torch.cuda.device(dev):
+        desc = _descriptor(g, noise, batch)
+        ws = _workspace(g, desc, batch, dev)
+        out = torch.empty(batch, size, size, 3, dtype=torch.uint8, device=dev)
+        ex = N.ForwardExtras()
+        ex.frames_u8, ex.u8_h, ex.u8_w = out.data_ptr(), size, size
+        N.check(N.lib().sgr_synthesis_forward_ex(C.byref(desc.struct), N.ptr(lat), batch, None, N.ptr(ws), ws.numel(), None,
+                                                 C.byref(ex), N.stream()), 'sgr_synthesis_forward_ex')
+    return out
+
+
 class _Synthesis(torch.autograd.Function):
     """Autograd node for dL/d(latent) — the only gradient the A-matrix training consumes (libs/trainer.py:144,187-189) —
     and, in train() mode, for the generator's own parameters (optimize_g, libs/optimization.py:25-72): those enter as
@@ -229,15 +253,33 @@ def run_synthesis(g, latent, noise, return_features=False):
         image, feats, _, _ = synthesis_forward(g, latent, noise, want_feats=True)
         return image, feats
     if torch.is_grad_enabled():
-        # train() mode (optimize_g): the generator's parameters are differentiable inputs; eval() mode: frozen generator
-        params = []
-        if g.training:
-            from .backward import synthesis_param_list
-            params = synthesis_param_list(g)
-            if not any(p.requires_grad for p in params):
-                params = []
-            elif any(n is None for n in noise):
-                raise RuntimeError('generator weight gradients need fixed noise buffers (randomize_noise=False)')
+        # Generator-parameter gradients (the reference's autograd forms them whenever a parameter requires grad, in train()
+        # and eval() mode alike).  Policy `g.param_grads`:
+        #   'auto' (default)  train() mode (optimize_g, libs/optimization.py:29): formed.  eval() mode with a latent that
+        #                     requires grad (A-matrix training, libs/trainer.py:111,144: G is never stepped): NOT formed — the
+        #                     weight-gradient GEMMs would double the backward for gradients nobody reads — with a one-time
+        #                     warning, so it is never a silent None; eval() mode with a constant latent: formed (the only
+        #                     thing backward() can be for).
+        #   'always'          exactly the reference: formed whenever any synthesis parameter requires grad.
+        #   'never'           latent gradient only.
+        # Freezing the generator (G.requires_grad_(False)) selects the latent-only path without any warning.
+        from .backward import synthesis_param_list
+        params = synthesis_param_list(g)
+        mode = getattr(g, 'param_grads', 'auto')
+        if mode not in ('auto', 'always', 'never'):
+            raise ValueError("Generator.param_grads must be 'auto', 'always' or 'never'")
+        any_req = any(p.requires_grad for p in params)
+        want = any_req and (mode == 'always' or (mode == 'auto' and (g.training or not latent.requires_grad)))
+        if any_req and not want and mode == 'auto' and not g.__dict__.get('_warned_frozen'):
+            import warnings
+            warnings.warn('Generator is in eval() mode with parameters that require grad: only dL/dlatent is computed, parameter '
+                          '.grad stays None (set G.param_grads = "always" for the reference behaviour, or G.requires_grad_(False) '
+                          'to silence this).', stacklevel=3)
+            g.__dict__['_warned_frozen'] = True
+        if want and any(n is None for n in noise):
+            raise RuntimeError('generator weight gradients need fixed noise buffers (randomize_noise=False)')
+        if not want:
+            params = []
         if latent.requires_grad or params:
             return _Synthesis.apply(latent, g, noise, *params)
     image, _, _, _ = synthesis_forward(g, latent, noise, want_feats=False)

@@ -366,6 +366,63 @@ def test_dlatent_vs_oracle_autograd(pkg, size, cm, batch):
     assert cos >= 0.9999, cos
 
 
+def _oracle_grad_with_masks(sd, wplus, size, cm, r, masks, dtype=torch.float64):
+    """dL/dlatent of L = sum(img * r) through the oracle in `dtype`, with the leaky-ReLU branch of every StyledConv taken
+    from `masks` (list of bool tensors, layer order) instead of the oracle's own sign: the derivative path of the GPU."""
+    sdd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    it = iter(masks)
+    orig = orc.fused_leaky_relu
+
+    def masked(x, bias, negative_slope=0.2, scale=orc.SQRT2):
+        v = x + bias.reshape([1, -1] + [1] * (x.ndim - 2))
+        return torch.where(next(it), v, v * negative_slope) * scale
+    orc.fused_leaky_relu = masked
+    try:
+        wr = wplus.to(dtype).clone().requires_grad_(True)
+        img, _ = orc.generator_forward(sdd, [wr], size, cm, input_is_latent=True)
+        (img * r.to(dtype)).sum().backward()
+    finally:
+        orc.fused_leaky_relu = orig
+    return wr.grad
+
+
+@pytest.mark.parametrize('size,cm,batch', [(32, 2, 3), (256, 1, 2)])
+def test_dlatent_shared_masks(pkg, size, cm, batch):
+    """Isolates the cause of the ~1e-2 end-to-end gradient deviation (test_dlatent_vs_oracle_autograd): the oracle's
+    fp64 backward driven by the sign masks of the GPU's OWN saved activations (the masks the GPU backward keys on,
+    op/fused_bias_act_kernel.cu:43) must agree with the GPU gradient to the config-4 bar, rel <= 1e-3 of max — what is
+    left of the end-to-end difference is then the flipped leaky-ReLU branches, not the backward arithmetic."""
+    sd = orc.seeded_state_dict(size, cm, seed=12)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    wplus = orc.seeded_wplus(sd, batch, G.n_latent, seed=21)
+    rng = np.random.Generator(np.random.PCG64(3))
+    r = T(rng.standard_normal((batch, 3, size, size), dtype=np.float32))
+    with torch.no_grad():
+        _, feats = G.synthesis(wplus.cuda(), return_features=True)
+    masks = [(f > 0).cpu() for f in feats]
+    wg = wplus.cuda().requires_grad_(True)
+    img, _ = G([wg], input_is_latent=True)
+    (img * r.cuda()).sum().backward()
+    ggpu = wg.grad.double().cpu()
+    g_shared = _oracle_grad_with_masks(sd, wplus, size, cm, r, masks)
+    with torch.no_grad():
+        _, _, ofeats = orc.generator_forward({k: v.double() if v.is_floating_point() else v for k, v in sd.items()},
+                                             [wplus.double()], size, cm, input_is_latent=True, return_features=True)
+    flips = sum(int(((of > 0) != m).sum()) for of, m in zip(ofeats, masks))
+    total = sum(m.numel() for m in masks)
+    g_own = _oracle_grad_with_masks(sd, wplus, size, cm, r, [(of > 0) for of in ofeats])
+    scale = float(g_own.abs().max())
+    e_shared = float((ggpu - g_shared).abs().max()) / scale
+    e_own = float((ggpu - g_own).abs().max()) / scale
+    e_flip = float((g_shared - g_own).abs().max()) / scale
+    print('\n[grad isolation %d^2 cm%d B%d] GPU vs fp64 oracle with GPU masks: %.2e | GPU vs fp64 oracle: %.2e | '
+          'oracle(GPU masks) vs oracle(own masks): %.2e | flipped masks %d of %d'
+          % (size, cm, batch, e_shared, e_own, e_flip, flips, total))
+    assert e_shared <= 1e-3, (e_shared, e_own, e_flip, flips)
+
+
 def test_backward_with_randomized_noise_is_consistent(pkg):
     """randomize_noise draws per-sample noise inside forward; backward must reuse exactly those maps."""
     size, cm = 32, 2
@@ -473,22 +530,86 @@ def test_single_pass_bf16_mode_reports_parity(pkg, monkeypatch):
     assert 1e-5 < e <= 2e-2 * rng_
 
 
-def test_frames_to_uint8_output_stage(pkg):
-    """fused clamp / scale / uint8 / HWC (+ 256-pooling) against the reference arithmetic.  Integer output:
-    bit-exact except where the fp32 value sits within one rounding of an integer boundary (division vs the oracle's)."""
+def test_frames_to_uint8_output_stage(pkg, golden):
+    """clamp / scale / uint8 / HWC (+ 256-pooling) with the reference arithmetic as it executes
+    (libs/utilities/image_utils.py:97-111 on the CPU copy run_inference.py:190-196 makes: fp32 clamp, +1, IEEE division by
+    float32(2.00001), *255, truncation by np.uint8; pooling = sequential fp32 sum over the window / area).  Byte output:
+    BIT-EXACT against the reference-generated golden and against the oracle on random frames, pooled and unpooled."""
+    g = golden('output_stage.npz')
+    xg = cuda(g['x'])
+    assert np.array_equal(pkg.frames_to_uint8(xg).cpu().numpy(), g['y'])
+    assert np.array_equal(pkg.frames_to_uint8(xg, size=8).cpu().numpy(), g['y_pooled'])
     rng = np.random.Generator(np.random.PCG64(31))
     x = T((rng.standard_normal((3, 3, 64, 64), dtype=np.float32) * 0.8))
     x[0, 0, 0, :4] = T(np.array([-1.0, 1.0, -3.0, 5.0], dtype=np.float32))
     y = pkg.frames_to_uint8(x.cuda()).cpu().numpy()
     ref = orc.frames_to_uint8(x)
     assert y.shape == ref.shape == (3, 64, 64, 3) and y.dtype == np.uint8
-    diff = np.abs(y.astype(np.int32) - ref.astype(np.int32))
-    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert np.array_equal(y, ref)
     assert y[0, 0, 0, 0] == 0 and y[0, 0, 1, 0] == 254 and y[0, 0, 2, 0] == 0 and y[0, 0, 3, 0] == 254   # (2/2.00001*255 -> 254)
-    yp = pkg.frames_to_uint8(x.cuda(), size=16).cpu().numpy()
-    refp = orc.frames_to_uint8(x, size=16)
-    dp = np.abs(yp.astype(np.int32) - refp.astype(np.int32))
-    assert yp.shape == (3, 16, 16, 3) and dp.max() <= 1 and (dp != 0).mean() < 2e-2
+    for size in (32, 16):                                     # 2x2 and 4x4 pooling windows (1024 -> 256 is 4x4)
+        yp = pkg.frames_to_uint8(x.cuda(), size=size).cpu().numpy()
+        assert yp.shape == (3, size, size, 3)
+        assert np.array_equal(yp, orc.frames_to_uint8(x, size=size)), size
+
+
+@pytest.mark.parametrize('size,cm,batch,out', [(64, 2, 3, 64), (64, 2, 2, 16), (256, 1, 2, 256)])
+def test_fused_uint8_frames_from_last_torgb(pkg, size, cm, batch, out):
+    """sgr_synthesis_forward_ex writes uint8 HWC frames from the last ToRGB tail (the fp32 frame is never
+    written).  Bit-exact against the two-pass path (fp32 frame -> sgr_frames_to_uint8) and against the reference
+    arithmetic (oracle.frames_to_uint8 on the CPU) applied to our own fp32 frame; pooled and unpooled."""
+    sd = orc.seeded_state_dict(size, cm, seed=4)
+    # random-init frames span +-10: scale every ToRGB so that the bytes are not all 0 / 254
+    for k in list(sd):
+        if k.startswith('to_rgb') and k.endswith('conv.weight'):
+            sd[k] = sd[k] * 0.05
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    w = orc.seeded_wplus(sd, batch, G.n_latent, seed=6).cuda()
+    with torch.no_grad():
+        img = G([w], input_is_latent=True)[0]
+        u8 = G.synthesis_uint8(w, size=out)
+    assert u8.shape == (batch, out, out, 3) and u8.dtype == torch.uint8
+    two_pass = pkg.frames_to_uint8(img, size=out)
+    assert torch.equal(u8, two_pass)
+    assert np.array_equal(u8.cpu().numpy(), orc.frames_to_uint8(img.cpu(), size=out))
+    vals = u8.cpu().numpy()
+    assert 0.02 < ((vals > 0) & (vals < 254)).mean(), 'test frames are saturated'
+    # the public glue: shift + truncation + bytes in one call
+    trunc = orc.seeded_wplus(sd, 1, 1, seed=5)[:, 0].cuda()
+    shift = 0.1 * torch.ones(batch, 2, 512, device='cuda')
+    a = pkg.generate_frames_uint8(G, w, 0.7, trunc, shift_code=shift, input_is_latent=True, size=out)
+    with torch.no_grad():
+        b = pkg.frames_to_uint8(pkg.generate_image(G, w, 0.7, trunc, shift_code=shift, input_is_latent=True), size=out)
+    assert torch.equal(a, b)
+
+
+def test_bench_workload_parity(pkg):
+    """The exact bench.py workload (BASELINE configs[2]): B=32, 256^2 / cm1, generate_image with the A(dp) shift on rows
+    0..7 + truncation 0.7, default kernel selection (fused-FIR producers, wrapped-halo scatter tiles) — sampled frames
+    against the oracle, pixel max-abs <= 1e-3 (north_star bar); the margin is printed."""
+    size, cm, batch = 256, 1, 32
+    sd = orc.seeded_state_dict(size, cm, seed=0)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    torch.manual_seed(5)
+    A = pkg.DirectionMatrix(512, input_dim=15, out_dim=512, w_plus=True, num_layers=8).cuda()
+    trunc = orc.seeded_wplus(sd, 1, 1, seed=7)[:, 0]
+    wsrc = orc.seeded_wplus(sd, 1, G.n_latent, seed=11).repeat(batch, 1, 1)
+    g = torch.Generator().manual_seed(4321)
+    dp = torch.rand(batch, 15, generator=g) * 6 - 3
+    with torch.no_grad():
+        img = pkg.generate_image(G, wsrc.cuda(), 0.7, trunc.cuda(), w_plus=True, num_layers_shift=8, shift_code=A(dp.cuda()),
+                                 input_is_latent=True).cpu()
+        rows = [0, 9, 22, 31]
+        shift = orc.direction_matrix_forward(A.linear.weight.cpu(), A.linear.bias.cpu(), dp[rows], 512, 8)
+        ref, _ = orc.generate_image(sd, wsrc[rows], 0.7, trunc, size, cm, shift_code=shift)
+    e = float((img[rows] - ref).abs().max())
+    print('\n[bench workload parity] 4 of 32 frames, pixel max-abs %.3e on range %.2f (bar 1e-3, margin x%.1f)'
+          % (e, float(ref.abs().max()), 1e-3 / max(e, 1e-12)))
+    assert e <= 1e-3, e
 
 
 def test_cuda_graph_replay_matches_eager_and_tracks_weight_updates(pkg):

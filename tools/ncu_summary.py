@@ -81,8 +81,64 @@ def full(src, dst_md, dst_json):
     print('wrote', dst_md, dst_json)
 
 
+def hbm(src, dst_md, peak_gbs=None):
+    """Per-launch table of the HBM-bound kernels: duration, DRAM bytes, achieved GB/s against the measured copy peak,
+    sectors per request of the global loads / stores."""
+    import os
+    if peak_gbs is None:
+        try:
+            peak_gbs = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                         'MEASURED_PEAKS.json')))['hbm_gbs'])
+        except Exception:
+            peak_gbs = 6650.0
+    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'dram__bytes_read.sum',
+            'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+            'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+            'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+            'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread']
+    ci = {k: (hdr.index(k) if k in hdr else None) for k in keys}
+
+    def num(r, k):
+        i = ci[k]
+        if i is None or r[i] in ('', 'n/a'):
+            return float('nan')
+        return float(r[i].replace(',', ''))
+
+    def scale(k, table):
+        return table.get(units[ci[k]].lower(), 1) if ci[k] is not None else 1
+    byte_u = {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}
+    time_u = {'ns': 1e-3, 'nsecond': 1e-3, 'us': 1, 'usecond': 1, 'ms': 1e3, 'msecond': 1e3, 'second': 1e6}
+    with open(dst_md, 'w') as f:
+        f.write('# `ncu --set full` of the HBM-bound kernels (tools/gpu_hbm_kernels.py)\n\n')
+        f.write('Command: `ncu --set full --clock-control none -k regex:"upfirdn2d_kernel|torgb_tail|bwd_act|up_bwd_prepare|'
+                'param_sums|frames_to_uint8" -o gpurun_out/prof_hbm python tools/gpu_hbm_kernels.py`; table = `ncu -i ... --page raw '
+                '--csv` through tools/ncu_summary.py hbm.  GB/s = (dram read + write bytes) / duration; peak = %.0f GB/s '
+                '(MEASURED_PEAKS.json copy bandwidth).  Durations under ncu are cold-cache.\n\n' % peak_gbs)
+        f.write('| kernel | grid | us | DRAM rd MB | DRAM wr MB | GB/s | of peak | DRAM % (ncu) | SM % | sectors/req ld | sectors/req st | regs |\n')
+        f.write('|---|---|---|---|---|---|---|---|---|---|---|---|\n')
+        for r in data:
+            name = r[ci['Kernel Name']].replace('void sgr::', '').replace('sgr::', '').split('(')[0]
+            us = num(r, 'gpu__time_duration.sum') * scale('gpu__time_duration.sum', time_u)
+            rd = num(r, 'dram__bytes_read.sum') * scale('dram__bytes_read.sum', byte_u)
+            wr = num(r, 'dram__bytes_write.sum') * scale('dram__bytes_write.sum', byte_u)
+            gbs = (rd + wr) / (us * 1e-6) / 1e9 if us > 0 else float('nan')
+            f.write('| `%s` | %d | %.1f | %.2f | %.2f | %.0f | %.2f | %.1f | %.1f | %.1f | %.1f | %d |\n' % (
+                name, num(r, 'launch__grid_size'), us, rd / 1e6, wr / 1e6, gbs, gbs / peak_gbs,
+                num(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
+                num(r, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'),
+                num(r, 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum') / max(num(r, 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum'), 1),
+                num(r, 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum') / max(num(r, 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum'), 1),
+                num(r, 'launch__registers_per_thread')))
+    print('wrote', dst_md)
+
+
 if __name__ == '__main__':
-    if sys.argv[1] == 'launches':
+    if sys.argv[1] == 'hbm':
+        hbm(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3], *([''] + sys.argv[4:5] if len(sys.argv) > 4 else []))
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4])
