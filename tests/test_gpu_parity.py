@@ -331,11 +331,13 @@ def test_reenact_dA_golden(pkg, golden):
     assert abs(loss.item() - float(g['loss'])) <= 1e-4 * max(1.0, abs(float(g['loss'])))
     G.zero_grad()
     loss.backward()
-    # Gradient tolerance: the leaky-relu derivative is discontinuous, so forward differences of ~2e-5 (tensor-core
-    # accumulate rounding) flip a few masks and move the gradient by ~1e-2 relative (tools/bwd_emulation_check.py
-    # reproduces this in fp64; the reference's own fp32 autograd is 2e-4..8e-4 away from fp64 for the same reason).
-    # Measured 0.7e-2 .. 1.01e-2 depending on the accumulation order of the forward kernels; bar 2e-2 as in
-    # test_dlatent_vs_oracle_autograd.
+    # Gradient tolerance.  The backward ARITHMETIC is accurate to ~1e-5 of max (test_dlatent_shared_masks: GPU vs the fp64
+    # oracle driven by the GPU's own leaky-ReLU masks: 7e-6 at 32^2, 1.3e-5 at 256^2 — the config-4 bar of 1e-3 with 100x
+    # margin).  End to end the derivative of leaky-ReLU is discontinuous: forward differences of ~2e-5 (tensor-core fp32
+    # accumulation order) put a handful of pre-activations on the other side of zero (measured: 14 of 4.2 M masks at 32^2, 90
+    # of 32 M at 256^2) and those few flipped branches move the gradient by 3.6e-3 .. 5.3e-3 of max — the SAME number the
+    # oracle shows against itself when only the masks are swapped (oracle(GPU masks) vs oracle(own masks)).  The reference's
+    # own fp32 CUDA autograd differs from fp64 the same way.  Bar for the end-to-end comparison: 2e-2 of max.
     assert err(A.linear.weight.grad, g['gA_w']) <= 2e-2 * np.abs(g['gA_w']).max()
     assert err(A.linear.bias.grad, g['gA_b']) <= 2e-2 * np.abs(g['gA_b']).max()
     assert all(p.grad is None for p in G.parameters())       # frozen generator: no weight gradients are formed
@@ -420,7 +422,8 @@ def test_dlatent_shared_masks(pkg, size, cm, batch):
     print('\n[grad isolation %d^2 cm%d B%d] GPU vs fp64 oracle with GPU masks: %.2e | GPU vs fp64 oracle: %.2e | '
           'oracle(GPU masks) vs oracle(own masks): %.2e | flipped masks %d of %d'
           % (size, cm, batch, e_shared, e_own, e_flip, flips, total))
-    assert e_shared <= 1e-3, (e_shared, e_own, e_flip, flips)
+    assert e_shared <= 2e-4, (e_shared, e_own, e_flip, flips)         # measured 0.7e-5 .. 1.3e-5; config-4 bar: 1e-3
+    assert abs(e_own - e_flip) <= 2e-4 + 0.05 * e_flip                # the end-to-end deviation IS the mask-flip term
 
 
 def test_backward_with_randomized_noise_is_consistent(pkg):
@@ -695,7 +698,7 @@ def test_modconv_wgrad_vs_aten_fp64(pkg, b, cin, cout, h, up):
     assert lib.sgr_modconv_wgrad(C.byref(a), N.stream()) != 0
 
 
-@pytest.mark.parametrize('size,cm,batch', [(8, 2, 2), (32, 2, 2)])
+@pytest.mark.parametrize('size,cm,batch', [(8, 2, 2), (32, 2, 2), (256, 1, 1)])
 def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
     """SURVEY 8f-1 (optimize_g, libs/optimization.py:25-72): in train() mode every parameter the synthesis path reads gets
     its gradient (conv / modulation / noise / bias of every StyledConv and ToRGB, the constant input) - against the oracle's
@@ -742,11 +745,36 @@ def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
         if n in native:
             scale = float(native[n].abs().max())
             assert float((p.grad - native[n]).abs().max()) <= 5e-3 * max(scale, 1e-6), n      # cuDNN wgrad runs in TF32
-    # eval() mode: the generator is frozen (A-matrix training): no parameter gradient is formed
+    # eval() mode with a latent that requires grad (A-matrix training): the generator stays frozen under the default policy,
+    # with a warning (never a silent None) ...
     G.zero_grad(set_to_none=True)
     G.eval()
+    G.__dict__.pop('_warned_frozen', None)
+    wg = wplus.cuda().requires_grad_(True)
+    with pytest.warns(UserWarning, match='eval\\(\\) mode'):
+        (G([wg], input_is_latent=True)[0] * r.cuda()).sum().backward()
+    assert wg.grad is not None and all(p.grad is None for p in G.parameters())
+    # ... param_grads = 'always' is the reference's behaviour (autograd populates every parameter in eval() mode too) ...
+    G.param_grads = 'always'
     wg = wplus.cuda().requires_grad_(True)
     (G([wg], input_is_latent=True)[0] * r.cuda()).sum().backward()
+    for n, p in G.named_parameters():
+        if n in native:
+            assert p.grad is not None and torch.equal(p.grad, native[n]), n        # same kernels as train() mode: bit-identical
+    # ... a constant latent in eval() mode forms them as well (backward() could be for nothing else) ...
+    G.param_grads = 'auto'
+    G.zero_grad(set_to_none=True)
+    (G([wplus.cuda()], input_is_latent=True)[0] * r.cuda()).sum().backward()
+    assert all(p.grad is not None for n, p in G.named_parameters() if n in native)
+    # ... and a frozen generator takes the latent-only path without any warning
+    G.zero_grad(set_to_none=True)
+    G.requires_grad_(False)
+    G.__dict__.pop('_warned_frozen', None)
+    import warnings
+    wg = wplus.cuda().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        (G([wg], input_is_latent=True)[0] * r.cuda()).sum().backward()
     assert wg.grad is not None and all(p.grad is None for p in G.parameters())
 
 
