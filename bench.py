@@ -280,9 +280,9 @@ def train_step_leg(pkg, G, trunc, device, rank, world, batch=16, steps=8, warm=3
     def step(use_heads):
         z_src = torch.randn(batch, 512, device=device, generator=g)
         z_tgt = torch.randn(batch, 512, device=device, generator=g)
-        with torch.no_grad():
-            src, w_src = pkg.generate_image(G, z_src, 0.7, trunc, input_is_latent=False, return_latents=True)
-            tgt = pkg.generate_image(G, z_tgt, 0.7, trunc, input_is_latent=False)
+        with torch.no_grad():              # source and target frames in ONE batched forward (the reference makes two calls)
+            both, w_both = pkg.generate_image(G, torch.cat([z_src, z_tgt]), 0.7, trunc, input_is_latent=False, return_latents=True)
+            src, tgt, w_src = both[:batch], both[batch:], w_both[:batch]
         dp = torch.rand(batch, 15, device=device, generator=g) * 6 - 3
         if use_heads:
             loss_fn = lambda img: heads(img, src, tgt)[0]                  # noqa: E731
@@ -411,6 +411,92 @@ def main():
     frames = BATCH * world * args.steps
     value = frames / (ms * 1e-3)
 
+    # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch), taken right after the
+    # headline region so that both see the same clocks (the 200-step `sustained` leg further down heats the part up)
+    roofline, layers = None, None
+    if rank == 0:
+        prof_steps = min(args.steps, 20)
+        lib.sgr_profile_enable(1)
+        lib.sgr_profile_collect(None, 0)
+        for i in range(prof_steps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 8192)()
+        tags = (ctypes.c_int * 8192)()
+        n = lib.sgr_profile_collect_tagged(buf, tags, 8192)
+        lib.sgr_profile_enable(0)
+        gemm_ms = [buf[i] for i in range(n) if tags[i] == 0]
+        fin_ms = [buf[i] for i in range(n) if tags[i] == 1]
+        per_step = len(gemm_ms) // prof_steps
+        fl = conv_flops_per_frame()
+        assert per_step == len(fl), (per_step, len(fl))
+        dur = [sum(gemm_ms[s * per_step + l] for s in range(prof_steps)) / prof_steps for l in range(per_step)]   # ms
+        pk = peaks()
+        total_ms = sum(dur)
+        total_fl = sum(fl) * BATCH
+        achieved = total_fl / (total_ms * 1e-3) / 1e12
+        issued = 3 * achieved                                      # bf16x3: 3 MMAs per product on every layer
+        # HBM-bound second pass of the upsampling layers: reads the fp32 parity planes, writes the hi/lo activations
+        fin_per_step = len(fin_ms) // prof_steps
+        fin_total = sum(fin_ms) / prof_steps
+        fin_bytes = 0
+        from oracle import stylegan2_oracle as orc
+        channels, log_size, _, _ = orc.synthesis_config(SIZE, CM)
+        up_bytes = []
+        for i in range(3, log_size + 1):
+            cout, h = channels[2 ** i], 2 ** (i - 1)
+            up_bytes.append(BATCH * cout * (4 * (h + 1) ** 2 * 4 + (2 * h) ** 2 * 4))
+        # the FIR pass of an up layer whose consumer is a resident-halo convolution (16^2 and larger) is applied by that
+        # convolution's producer warps (csrc/fir_producer.cuh; SGR_FUSE_FIR=0 disables): only the first fin_per_step
+        # (smallest) up layers still launch the separate pass
+        fin_bytes = sum(up_bytes[:fin_per_step])
+        roofline = {'bound': 'tensor',
+                    'kernel': 'tcgen05 conv kernels: modconv / modconv_halo / upconv_scatter (%d launches/step)' % per_step,
+                    'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
+                    'traffic': ncu_traffic_bytes(),
+                    'issued_tflops': issued, 'issued_frac': issued / pk['bf16'], 'peak_source': pk['src'],
+                    'peak_burst': pk['bf16_burst'], 'frac_vs_burst': achieved / pk['bf16_burst'],
+                    'issued_frac_vs_burst': issued / pk['bf16_burst'],
+                    'peak_note': 'frac / issued_frac are against the SUSTAINED cuBLAS bf16 figure of MEASURED_PEAKS.json (the timed '
+                                 'region sits inside a long run of back-to-back steps: see `sustained`); *_vs_burst against the burst figure',
+                    'note': 'achieved = algorithmic conv FLOPs (SURVEY 8d, 29.746 GFLOP/frame) / summed CUDA-event time of '
+                            'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
+                            'comparable to the bf16 dense peak',
+                    'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps),
+                    'fused_fir_note': 'the convolution launches that follow an up layer also apply that layer\'s 4x4 FIR + '
+                                      'epilogue pass in producer warps (csrc/fir_producer.cuh), so their duration includes it; '
+                                      'SGR_FUSE_FIR=0 separates the pass again (conv kernels 8 % faster, step 5 % slower)',
+                    'step_algorithmic_tflops': total_fl / (ms / args.steps * 1e-3) / 1e12,
+                    'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step; %d up layers have their FIR pass fused into '
+                                           'the consumer convolution)' % (fin_per_step, len(up_bytes) - fin_per_step),
+                                 'bound': 'hbm',
+                                 'ms_per_step': fin_total, 'algorithmic_bytes': fin_bytes,
+                                 'achieved': fin_bytes / (fin_total * 1e-3) / 1e9 if fin_total > 0 else None,
+                                 'peak': pk['hbm'], 'unit': 'GB/s',
+                                 'frac': fin_bytes / (fin_total * 1e-3) / 1e9 / pk['hbm'] if fin_total > 0 else None}}
+        layers = [{'layer': l, 'ms': round(d, 4), 'algo_tflops': round(f * BATCH / (d * 1e-3) / 1e12, 2)}
+                  for l, (d, f) in enumerate(zip(dur, fl))]
+        if fin_per_step < len(up_bytes):
+            roofline['hbm_pass']['note'] = ('only the smallest up layers still run the separate pass (launch-latency bound at '
+                                            'this size); the others are fused into their consumer, see fused_fir_note')
+        # the same measurement with the FIR pass as a separate kernel (the GEMM kernels alone), in a child process: the
+        # switch is read once per process
+        if world == 1 and os.environ.get('SGR_FUSE_FIR', '1') != '0' and not os.environ.get('SGR_BENCH_CHILD'):
+            import subprocess
+            try:
+                env = dict(os.environ, SGR_FUSE_FIR='0', SGR_BENCH_CHILD='1')
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--steps', '10', '--warmup', '3',
+                                      '--cpu-baseline', '0'], env=env, capture_output=True, text=True, timeout=300).stdout
+                ch = json.loads(out.strip().splitlines()[-1])
+                roofline['separate_fir_pass'] = {
+                    'ms_per_step': ch['ms_per_step'], 'value': ch['value'], 'conv_kernel_ms_per_step': ch['roofline']['kernel_ms_per_step'],
+                    'achieved': ch['roofline']['achieved'], 'frac': ch['roofline']['frac'], 'issued_frac': ch['roofline']['issued_frac'],
+                    'hbm_pass': ch['roofline']['hbm_pass'],
+                    'note': 'SGR_FUSE_FIR=0: GEMM kernels without the fused FIR producers + the HBM-bound up_finish_kernel pass'}
+            except Exception as e:  # noqa: BLE001  (informational leg only)
+                roofline['separate_fir_pass'] = {'error': str(e)[:200]}
+
+
     # ---- end to end: dp from pinned host memory, frames back to pinned host memory, every step
     out_host = [torch.empty(BATCH, 3, SIZE, SIZE).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=device)
@@ -494,90 +580,6 @@ def main():
 
     # ---- configs[3]: A-matrix train step, B=16 per GPU, surrogate loss heads, all-reduce of A's gradient
     train = train_step_leg(pkg, G, trunc, device, rank, world) if args.train else None
-
-    # ---- per-launch timing of the modconv kernel (extra steps with event pairs around every launch)
-    roofline, layers = None, None
-    if rank == 0:
-        prof_steps = min(args.steps, 10)
-        lib.sgr_profile_enable(1)
-        lib.sgr_profile_collect(None, 0)
-        for i in range(prof_steps):
-            step_resident(i)
-        torch.cuda.synchronize()
-        buf = (ctypes.c_float * 8192)()
-        tags = (ctypes.c_int * 8192)()
-        n = lib.sgr_profile_collect_tagged(buf, tags, 8192)
-        lib.sgr_profile_enable(0)
-        gemm_ms = [buf[i] for i in range(n) if tags[i] == 0]
-        fin_ms = [buf[i] for i in range(n) if tags[i] == 1]
-        per_step = len(gemm_ms) // prof_steps
-        fl = conv_flops_per_frame()
-        assert per_step == len(fl), (per_step, len(fl))
-        dur = [sum(gemm_ms[s * per_step + l] for s in range(prof_steps)) / prof_steps for l in range(per_step)]   # ms
-        pk = peaks()
-        total_ms = sum(dur)
-        total_fl = sum(fl) * BATCH
-        achieved = total_fl / (total_ms * 1e-3) / 1e12
-        issued = 3 * achieved                                      # bf16x3: 3 MMAs per product on every layer
-        # HBM-bound second pass of the upsampling layers: reads the fp32 parity planes, writes the hi/lo activations
-        fin_per_step = len(fin_ms) // prof_steps
-        fin_total = sum(fin_ms) / prof_steps
-        fin_bytes = 0
-        from oracle import stylegan2_oracle as orc
-        channels, log_size, _, _ = orc.synthesis_config(SIZE, CM)
-        up_bytes = []
-        for i in range(3, log_size + 1):
-            cout, h = channels[2 ** i], 2 ** (i - 1)
-            up_bytes.append(BATCH * cout * (4 * (h + 1) ** 2 * 4 + (2 * h) ** 2 * 4))
-        # the FIR pass of an up layer whose consumer is a resident-halo convolution (16^2 and larger) is applied by that
-        # convolution's producer warps (csrc/fir_producer.cuh; SGR_FUSE_FIR=0 disables): only the first fin_per_step
-        # (smallest) up layers still launch the separate pass
-        fin_bytes = sum(up_bytes[:fin_per_step])
-        roofline = {'bound': 'tensor',
-                    'kernel': 'tcgen05 conv kernels: modconv / modconv_halo / upconv_scatter (%d launches/step)' % per_step,
-                    'achieved': achieved, 'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16'],
-                    'traffic': ncu_traffic_bytes(),
-                    'issued_tflops': issued, 'issued_frac': issued / pk['bf16'], 'peak_source': pk['src'],
-                    'peak_burst': pk['bf16_burst'], 'frac_vs_burst': achieved / pk['bf16_burst'],
-                    'issued_frac_vs_burst': issued / pk['bf16_burst'],
-                    'peak_note': 'frac / issued_frac are against the SUSTAINED cuBLAS bf16 figure of MEASURED_PEAKS.json (the timed '
-                                 'region sits inside a long run of back-to-back steps: see `sustained`); *_vs_burst against the burst figure',
-                    'note': 'achieved = algorithmic conv FLOPs (SURVEY 8d, 29.746 GFLOP/frame) / summed CUDA-event time of '
-                            'the launches; fp32 parity issues 3 bf16 MMAs per product, so issued = 3 x achieved is the number '
-                            'comparable to the bf16 dense peak',
-                    'kernel_ms_per_step': total_ms, 'kernel_share_of_step': total_ms / (ms / args.steps),
-                    'fused_fir_note': 'the convolution launches that follow an up layer also apply that layer\'s 4x4 FIR + '
-                                      'epilogue pass in producer warps (csrc/fir_producer.cuh), so their duration includes it; '
-                                      'SGR_FUSE_FIR=0 separates the pass again (conv kernels 8 % faster, step 5 % slower)',
-                    'step_algorithmic_tflops': total_fl / (ms / args.steps * 1e-3) / 1e12,
-                    'hbm_pass': {'kernel': 'up_finish_kernel (%d launches/step; %d up layers have their FIR pass fused into '
-                                           'the consumer convolution)' % (fin_per_step, len(up_bytes) - fin_per_step),
-                                 'bound': 'hbm',
-                                 'ms_per_step': fin_total, 'algorithmic_bytes': fin_bytes,
-                                 'achieved': fin_bytes / (fin_total * 1e-3) / 1e9 if fin_total > 0 else None,
-                                 'peak': pk['hbm'], 'unit': 'GB/s',
-                                 'frac': fin_bytes / (fin_total * 1e-3) / 1e9 / pk['hbm'] if fin_total > 0 else None}}
-        layers = [{'layer': l, 'ms': round(d, 4), 'algo_tflops': round(f * BATCH / (d * 1e-3) / 1e12, 2)}
-                  for l, (d, f) in enumerate(zip(dur, fl))]
-        if fin_per_step < len(up_bytes):
-            roofline['hbm_pass']['note'] = ('only the smallest up layers still run the separate pass (launch-latency bound at '
-                                            'this size); the others are fused into their consumer, see fused_fir_note')
-        # the same measurement with the FIR pass as a separate kernel (the GEMM kernels alone), in a child process: the
-        # switch is read once per process
-        if world == 1 and os.environ.get('SGR_FUSE_FIR', '1') != '0' and not os.environ.get('SGR_BENCH_CHILD'):
-            import subprocess
-            try:
-                env = dict(os.environ, SGR_FUSE_FIR='0', SGR_BENCH_CHILD='1')
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), '--steps', '10', '--warmup', '3',
-                                      '--cpu-baseline', '0'], env=env, capture_output=True, text=True, timeout=300).stdout
-                ch = json.loads(out.strip().splitlines()[-1])
-                roofline['separate_fir_pass'] = {
-                    'ms_per_step': ch['ms_per_step'], 'value': ch['value'], 'conv_kernel_ms_per_step': ch['roofline']['kernel_ms_per_step'],
-                    'achieved': ch['roofline']['achieved'], 'frac': ch['roofline']['frac'], 'issued_frac': ch['roofline']['issued_frac'],
-                    'hbm_pass': ch['roofline']['hbm_pass'],
-                    'note': 'SGR_FUSE_FIR=0: GEMM kernels without the fused FIR producers + the HBM-bound up_finish_kernel pass'}
-            except Exception as e:  # noqa: BLE001  (informational leg only)
-                roofline['separate_fir_pass'] = {'error': str(e)[:200]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_baseline:

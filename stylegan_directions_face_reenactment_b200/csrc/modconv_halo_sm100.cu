@@ -288,6 +288,24 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
                             (p.debug & 64) ? idesc_cat : idesc, 1);                           // lo*hi
                 }
               }
+            } else if (!Cfg::kConcat && !p.single && MT > 1 && !(p.debug & 128)) {
+              // consecutive MMAs alternate between the sub-tiles' accumulators: an MMA that accumulates into the TMEM columns
+              // of its predecessor waits ~43 cycles for it (tools/microbench/mma_rate.cu: N=128 107 cycles in one chain, 64 when
+              // two chains alternate); debug 128 = the old order (three products of one sub-tile back to back)
+#pragma unroll
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint64_t b_hi = umma_desc(b_addr + j * 2 * kBLbo, kBLbo, 128);
+                const uint64_t b_lo = umma_desc(b_addr + kBPlane + j * 2 * kBLbo, kBLbo, 128);
+#pragma unroll
+                for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t a_off = a_addr + tap_off + mt * 128 + j * 2 * kALbo + (prod == 0 ? kAPlane : 0);
+                    umma_bf16(d_tmem + mt * NT, umma_desc(a_off, kALbo, kASbo), prod == 1 ? b_lo : b_hi, idesc,
+                              prod != 0 || kb > kb0 || (tap | j) != 0);          // lo*hi, hi*lo, hi*hi
+                  }
+                }
+              }
             } else {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {

@@ -1,5 +1,7 @@
 // HBM-bound kernels: upfirdn2d (replaces op/upfirdn2d_kernel.cu:52-272), fused bias + leaky-relu
 // (replaces op/fused_bias_act_kernel.cu:18-99) and the ToRGB tail (bias + 2x FIR-upsampled skip, model.py:355-359).
+#include <stdlib.h>
+
 #include "sgr_internal.h"
 
 namespace sgr {
@@ -92,6 +94,166 @@ __global__ void upfirdn2d_kernel(const float* __restrict__ x, float* __restrict_
   }
 }
 
+// up == down == 1 with a 4x4 FIR (the Blur after an up-conv, model.py:72-88; the mode that moves the most bytes): row-walking
+// variant.  A thread owns VX = 4 adjacent output columns and walks ROWS output rows downwards with a 4-row register window,
+// so every input element is loaded ONCE (the kernel above re-reads each input row for its four output rows and re-does the
+// halo shuffles: ~30 instructions per output, issue-bound at 27 % of the HBM rate); per output row: 4 loads (issued PF rows
+// ahead: the walk is a dependent chain, without the prefetch the kernel is latency-bound), 3 halo shuffles from the lane to
+// the right, the FMAs and one 16-byte store.  When the taps are an outer product gy (x) gx (checked in the kernel; always the
+// case for make_kernel's FIRs) the FIR runs separably: horizontal pass on the incoming row (4 FMAs / output), vertical
+// pass over the window of row results (4 FMAs / output) instead of 16.
+template <bool SEP, int ROWS>
+__device__ __forceinline__ void upfirdn2d_rows_body(const float* __restrict__ x, float* __restrict__ y, const float* sk, int planes,
+                                                    int in_h, int in_w, int out_h, int out_w, int pad0) {
+  constexpr int VX = 4, K = 4, PF = 3;
+  const int lane = threadIdx.x & 31;
+  const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * VX;
+  const int oy0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;
+  if (oy0 >= out_h) return;                                  // whole warps (blockDim.x is a multiple of 32)
+  const bool col_ok = ox0 < out_w;
+  const bool vec_ok = (out_w % 4) == 0;
+  float gy[K], gx[K], t2[K][K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    gy[i] = SEP ? sk[K * K + i] : 0.f;
+    gx[i] = SEP ? sk[K * K + K + i] : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) t2[i][j] = SEP ? 0.f : sk[i * K + j];
+  }
+  const int rows = min(ROWS, out_h - oy0);
+  const int n_in = rows + K - 1;                             // input rows oy0 - pad0 .. oy0 + rows + K - 2 - pad0
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const float* xp = x + static_cast<size_t>(pl) * in_h * in_w;
+    float* yp = y + static_cast<size_t>(pl) * out_h * out_w;
+    // raw row r: the lane's VX values + (lane 31 only) the K-1 values right of them
+    auto load_row = [&](int r, float (&own)[VX], float (&edge)[K - 1]) {
+      const int iy = oy0 + r - pad0;
+      const bool row_ok = r < n_in && iy >= 0 && iy < in_h;  // warp-uniform
+#pragma unroll
+      for (int v = 0; v < VX; ++v) {
+        const int ix = ox0 + v - pad0;
+        own[v] = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
+      }
+#pragma unroll
+      for (int h = 0; h < K - 1; ++h) {
+        const int ix = ox0 + VX + h - pad0;
+        edge[h] = (lane == 31 && row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
+      }
+    };
+    float q_own[PF][VX], q_edge[PF][K - 1];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) load_row(i, q_own[i], q_edge[i]);
+    // window of the last K rows: SEP keeps horizontally filtered rows (VX values), otherwise raw rows (VX + K - 1 values)
+    float win[K][SEP ? VX : VX + K - 1];
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int j = 0; j < (SEP ? VX : VX + K - 1); ++j) win[i][j] = 0.f;
+#pragma unroll 1
+    for (int r0 = 0; r0 < n_in; r0 += PF) {
+#pragma unroll
+      for (int s = 0; s < PF; ++s) {
+        const int r = r0 + s;
+        float raw[VX + K - 1];
+#pragma unroll
+        for (int v = 0; v < VX; ++v) raw[v] = q_own[s][v];
+#pragma unroll
+        for (int h = 0; h < K - 1; ++h) {                   // halo: the first K-1 values of the lane to the right
+          const float nb = __shfl_down_sync(0xffffffffu, q_own[s][h], 1);
+          raw[VX + h] = lane == 31 ? q_edge[s][h] : nb;
+        }
+        load_row(r + PF, q_own[s], q_edge[s]);              // refill the slot: PF rows in flight
+        if (r < n_in) {
+#pragma unroll
+          for (int i = 0; i < K - 1; ++i)
+#pragma unroll
+            for (int j = 0; j < (SEP ? VX : VX + K - 1); ++j) win[i][j] = win[i + 1][j];
+          if (SEP) {
+#pragma unroll
+            for (int v = 0; v < VX; ++v)
+              win[K - 1][v] = fmaf(gx[3], raw[v + 3], fmaf(gx[2], raw[v + 2], fmaf(gx[1], raw[v + 1], gx[0] * raw[v])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < VX + K - 1; ++j) win[K - 1][j] = raw[j];
+          }
+          if (r >= K - 1 && col_ok) {
+            const int oy = oy0 + r - (K - 1);
+            float acc[VX];
+#pragma unroll
+            for (int v = 0; v < VX; ++v) {
+              if (SEP) {
+                acc[v] = fmaf(gy[3], win[3][v], fmaf(gy[2], win[2][v], fmaf(gy[1], win[1][v], gy[0] * win[0][v])));
+              } else {
+                float a = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                  for (int kx = 0; kx < K; ++kx) a = fmaf(t2[ky][kx], win[ky][v + kx], a);
+                acc[v] = a;
+              }
+            }
+            float* dst = yp + static_cast<size_t>(oy) * out_w + ox0;
+            if (vec_ok) {
+              *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < VX; ++v)
+                if (ox0 + v < out_w) dst[v] = acc[v];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256) upfirdn2d_rows_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             const float* __restrict__ taps, int planes, int in_h, int in_w,
+                                                             int out_h, int out_w, int pad0, int allow_sep) {
+  constexpr int K = 4;
+  __shared__ float sk[K * K + 2 * K];
+  __shared__ int sep;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    // flipped taps; separable form gy[ky] * gx[kx] with gy = row sums, gx = column sums / total; exact rank-1 test (tolerance
+    // 1e-6 of the largest tap, as the host check of the scatter path, model.py up_mode())
+    float tot = 0.f, mx = 0.f;
+    for (int i = 0; i < K * K; ++i) {
+      sk[i] = taps[(K - 1 - i / K) * K + (K - 1 - i % K)];
+      tot += sk[i];
+      mx = fmaxf(mx, fabsf(sk[i]));
+    }
+    for (int a = 0; a < K; ++a) {
+      float rs = 0.f, cs = 0.f;
+      for (int i = 0; i < K; ++i) {
+        rs += sk[a * K + i];
+        cs += sk[i * K + a];
+      }
+      sk[K * K + a] = rs;
+      sk[K * K + K + a] = tot != 0.f ? cs / tot : 0.f;
+    }
+    float dev = 0.f;
+    for (int i = 0; i < K * K; ++i) dev = fmaxf(dev, fabsf(sk[i] - sk[K * K + i / K] * sk[K * K + K + i % K]));
+    sep = (allow_sep && tot != 0.f && dev <= 1e-6f * mx) ? 1 : 0;
+  }
+  __syncthreads();
+  if (sep)
+    upfirdn2d_rows_body<true, ROWS>(x, y, sk, planes, in_h, in_w, out_h, out_w, pad0);
+  else
+    upfirdn2d_rows_body<false, ROWS>(x, y, sk, planes, in_h, in_w, out_h, out_w, pad0);
+}
+
+static void launch_ufd_rows(const float* x, float* y, const float* taps, int planes, int in_h, int in_w, int out_h, int out_w,
+                            int pad0, int allow_sep, cudaStream_t st) {
+  constexpr int ROWS = 32;
+  const int tx = out_w >= 4 * 64 ? 64 : 32;                   // threads along x (4 outputs each)
+  const int strips = (out_h + ROWS - 1) / ROWS;
+  const int ty = strips >= 4 ? 4 : (strips >= 2 ? 2 : 1);
+  dim3 block(tx, ty);
+  dim3 grid((out_w + tx * 4 - 1) / (tx * 4), (strips + ty - 1) / ty, planes < 65535 ? planes : 65535);
+  upfirdn2d_rows_kernel<ROWS><<<grid, block, 0, st>>>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, allow_sep);
+}
+
 // Any factors / tap counts (correctness path for shapes outside the generator's four modes).
 __global__ void upfirdn2d_generic_kernel(const float* __restrict__ x, float* __restrict__ y,
                                          const float* __restrict__ taps, int planes, int in_h, int in_w, int out_h,
@@ -136,7 +298,13 @@ int upfirdn2d_launch(const float* x, float* y, const float* taps, int planes, in
     return 1;
   }
   if (kh == 4 && kw == 4 && out_h <= 65535 && up == 1 && down == 1) {
-    launch_ufd44<1, 1>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
+    // SGR_UPFIRDN_ROWS: 0 = the per-row kernel, 1 = row-walking kernel with the 16-tap arithmetic only, default 2 = row-walking,
+    // separable arithmetic when the taps are an outer product
+    static const int rows_mode = [] { const char* e = getenv("SGR_UPFIRDN_ROWS"); return e ? atoi(e) : 2; }();
+    if (rows_mode == 0)
+      launch_ufd44<1, 1>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
+    else
+      launch_ufd_rows(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, rows_mode == 2 ? 1 : 0, st);
   } else if (kh == 4 && kw == 4 && out_h <= 65535 && up == 2 && down == 1) {
     launch_ufd44<2, 1>(x, y, taps, planes, in_h, in_w, out_h, out_w, pad0, st);
   } else if (kh == 4 && kw == 4 && out_h <= 65535 && up == 1 && down == 2) {

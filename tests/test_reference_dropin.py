@@ -150,8 +150,11 @@ def test_native_ops_against_the_reference_cuda_ops(ref_env):
         assert torch.allclose(xo.grad, xr.grad, rtol=2.4e-7, atol=0), shape
         assert float((bo.grad - br.grad).abs().max()) <= 2e-5 * float(br.grad.abs().max()), shape      # reduction order
     fir = orc.make_fir_kernel([1, 3, 3, 1]).cuda() * 4
+    errs = []
     for shape, up, down, pad in [((3, 7, 65, 65), 1, 1, (1, 1)), ((2, 3, 128, 128), 2, 1, (2, 1)), ((2, 3, 256, 256), 1, 2, (1, 1)),
-                                 ((1, 2, 257, 257), 1, 1, (1, 1)), ((2, 5, 16, 24), 2, 2, (2, 2))]:
+                                 ((1, 2, 257, 257), 1, 1, (1, 1)), ((1, 3, 33, 65), 1, 1, (2, 2))]:
+        # (the reference's CUDA op has kernels for these factor combinations only: any other, e.g. up = down = 2, falls through
+        #  its `switch (mode)` and returns uninitialised memory, op/upfirdn2d_kernel.cu:223-270)
         x = torch.randn(*shape, device='cuda', generator=g)
         xr = x.clone().requires_grad_(True)
         yr = ref_upfirdn2d(xr, fir, up=up, down=down, pad=pad)
@@ -161,5 +164,8 @@ def test_native_ops_against_the_reference_cuda_ops(ref_env):
         yo = pkg.upfirdn2d(xo, fir, up=up, down=down, pad=pad)
         yo.backward(gy)
         assert yo.shape == yr.shape
-        assert float((yo - yr).abs().max()) <= 5e-6, (shape, up, down)
-        assert float((xo.grad - xr.grad).abs().max()) <= 5e-6, (shape, up, down)
+        ef = float((yo.detach() - yr.detach()).abs().max()) / float(yr.detach().abs().max())
+        eb = float((xo.grad - xr.grad).abs().max()) / float(xr.grad.abs().max())
+        print('[upfirdn2d vs reference CUDA op] %s up %d down %d pad %s: fwd %.2e bwd %.2e (relative to max)' % (shape, up, down, pad, ef, eb))
+        errs.append((shape, up, down, ef, eb))
+    assert all(ef <= 2e-6 and eb <= 2e-6 for _, _, _, ef, eb in errs), errs       # fp32 sums of 16 taps in a different order

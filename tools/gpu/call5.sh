@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== mma patterns"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mma_rate tools/microbench/mma_rate.cu && /tmp/mma_rate p 2>&1 | tee gpurun_out/mma_patterns.log
+echo "== upfirdn2d kernels"
+for m in 0 1 2; do SGR_UPFIRDN_ROWS=$m python tools/gpu_upfirdn_bench.py; done
+echo "== tests (upfirdn / ops)"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_reference_dropin.py -m gpu -q -s -k "upfirdn or native_ops or styled_block or generator_small" 2>&1 | grep -v "^$" | tail -14
+SGR_UPFIRDN_ROWS=2 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "upfirdn" 2>&1 | tail -3

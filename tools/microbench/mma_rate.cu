@@ -17,6 +17,9 @@ struct Case {
   int n2;         // second MMA shape interleaved (0 = none): alternating N / N2 on different columns
   int lsu;        // 1: warps 4..7 stream LDS.128 over 64 KiB concurrently (shared-memory pressure of producer warps)
   int iters;
+  int a_rot;      // distinct A operands in rotation (1: every MMA re-reads the same A; 4: as a real K loop / tap loop does)
+  int b_rot;      // distinct B operands in rotation
+  int acc_rot;    // accumulators (TMEM column ranges) in rotation: 1 = one dependent accumulation chain
 };
 
 __global__ void __launch_bounds__(256, 1) mma_rate_kernel(Case c, unsigned long long* out_cycles, unsigned long long* out_ns,
@@ -56,9 +59,19 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(Case c, unsigned long 
     mbar_wait(bar, 0);
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
     t0 = clock64();
-    for (int i = 0; i < c.iters; ++i) {
-      umma_bf16(tmem, adesc, bdesc, idesc, 1);
-      if (c.n2) umma_bf16(tmem + 256, adesc, bdesc, idesc2, 1);
+    uint64_t ad[4], bd[4];
+    uint32_t tm[4];
+    for (int k = 0; k < 4; ++k) {
+      ad[k] = adesc + (((k % c.a_rot) * 6144) >> 4);           // distinct A tiles 6 KiB apart (inside the 16 KiB k-slice)
+      bd[k] = bdesc + (((k % c.b_rot) * 8192) >> 4);           // distinct B slabs
+      tm[k] = tmem + (k % c.acc_rot) * (512 / c.acc_rot);
+    }
+    for (int i = 0; i < c.iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_bf16(tm[k], ad[k], bd[k], idesc, 1);
+        if (c.n2) umma_bf16(tm[k] + 256, ad[(k + 1) & 3], bd[k], idesc2, 1);
+      }
     }
     umma_commit(bar);
     mbar_wait(bar, 1);
@@ -88,7 +101,146 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(Case c, unsigned long 
   }
 }
 
-int main() {
+// ---- v3/v4: repeating PATTERNS of up to 8 MMAs (shape N, TMEM column offset, B slab index + row offset, A tile index), fully
+// unrolled at compile time (a runtime-length pattern loop is issue-bound at ~330 cycles per iteration).  Operands rotate
+// through 4 distinct A tiles and 4 distinct B slabs per repetition, as a real K / tap loop does.
+struct Pattern {
+  int np;
+  int n[8], col[8], bslab[8], brow[8], aidx[8];
+  int iters;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256, 1) mma_pattern_kernel(Pattern c, unsigned long long* out_cycles, unsigned long long* out_ns) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  uint8_t* a_base = smem + 1024;                 // 4 A tiles x (2 k-slices x 8 KiB) = 64 KiB
+  uint8_t* b_base = a_base + 64 * 1024;          // 4 B slabs x (2 k-slices x 8 KiB) = 64 KiB (N <= 512 rows per slice)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_base)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 1 && lane == 0) {
+    // rep r of the pattern uses A tile (aidx + r) % 4 and B slab (bslab + r) % 4
+    uint64_t ad[4][NP], bd[4][NP];
+    uint32_t id[NP], tm[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      id[k] = umma_idesc(kFmtBF16, 128, c.n[k]);
+      tm[k] = tmem + c.col[k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        ad[r][k] = umma_desc(smem_u32(a_base) + ((c.aidx[k] + r) & 3) * 16384, 8192, 256);        // 16-pixel rows (dense 256 B pitch)
+        bd[r][k] = umma_desc(smem_u32(b_base) + ((c.bslab[k] + r) & 3) * 16384 + c.brow[k] * 16, 8192, 128);
+      }
+    }
+    unsigned long long t0, t1, n0, n1;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < NP; ++k) umma_bf16(tm[k], ad[i & 3][k], bd[i & 3][k], id[k], i != 0);
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
+    t0 = clock64();
+    for (int i = 0; i < c.iters; i += 4) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < NP; ++k) umma_bf16(tm[k], ad[r][k], bd[r][k], id[k], 1);
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 1);
+    t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+    out_cycles[blockIdx.x] = t1 - t0;
+    out_ns[blockIdx.x] = n1 - n0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int NP>
+static void launch_pattern(const Pattern& p, int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
+  cudaFuncSetAttribute(mma_pattern_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mma_pattern_kernel<NP><<<sms, 256, smem>>>(p, cyc, ns);
+}
+
+static void run_patterns(int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
+  struct Named { const char* name; Pattern p; };
+  const int it = 8000;
+  // fields: np, n[], col[], bslab[], brow[], aidx[]
+  std::vector<Named> ps = {
+      {"N=256 stream, one accumulator", {1, {256}, {0}, {0}, {0}, {0}, it}},
+      {"N=256 x2: same A, two B slabs, two accumulators", {2, {256, 256}, {0, 256}, {0, 1}, {0, 0}, {0, 0}, it}},
+      {"N=256 x2: two A, same B, two accumulators (MT=2)", {2, {256, 256}, {0, 256}, {0, 0}, {0, 0}, {0, 1}, it}},
+      {"N=256 x3 lh hl hh (current halo<256,1> order)", {3, {256, 256, 256}, {0, 0, 0}, {0, 1, 0}, {0, 0, 0}, {1, 0, 0}, it}},
+      {"N=256 x3 hl hh lh (A shared, then B shared)", {3, {256, 256, 256}, {0, 0, 0}, {1, 0, 0}, {0, 0, 0}, {0, 0, 1}, it}},
+      {"N=128 stream, one accumulator", {1, {128}, {0}, {0}, {0}, {0}, it}},
+      {"N=128 x2: same A, B halves of one slab, acc halves (N=256 split)", {2, {128, 128}, {0, 128}, {0, 0}, {0, 128}, {0, 0}, it}},
+      {"N=128 x2: same A, same acc, two B (K-like)", {2, {128, 128}, {0, 0}, {0, 1}, {0, 0}, {0, 0}, it}},
+      {"N=128 x2: two A, same B, two acc (MT=2 interleave)", {2, {128, 128}, {0, 128}, {0, 0}, {0, 0}, {0, 1}, it}},
+      {"N=128 x2: two A, two B, two acc", {2, {128, 128}, {0, 128}, {0, 1}, {0, 0}, {0, 1}, it}},
+      {"N=128 x2: same A, same B, two acc", {2, {128, 128}, {0, 128}, {0, 0}, {0, 0}, {0, 0}, it}},
+      {"3 products as N=128 halves: lh lh' hl hl' hh hh'", {6, {128, 128, 128, 128, 128, 128}, {0, 128, 0, 128, 0, 128}, {0, 0, 1, 1, 0, 0}, {0, 128, 0, 128, 0, 128}, {1, 1, 0, 0, 0, 0}, it}},
+      {"halo<128,2> new order: lh0 lh1 hl0 hl1 hh0 hh1", {6, {128, 128, 128, 128, 128, 128}, {0, 128, 0, 128, 0, 128}, {0, 0, 1, 1, 0, 0}, {0, 0, 0, 0, 0, 0}, {1, 3, 0, 2, 0, 2}, it}},
+      {"halo<128,2> old order: lh0 hl0 hh0 lh1 hl1 hh1", {6, {128, 128, 128, 128, 128, 128}, {0, 0, 0, 128, 128, 128}, {0, 1, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 0}, {1, 0, 0, 3, 2, 2}, it}},
+      {"scatter 256,128,128,64 (4 A tiles, one acc)", {4, {256, 128, 128, 64}, {0, 0, 64, 64}, {0, 1, 2, 3}, {0, 0, 0, 0}, {0, 1, 2, 3}, it}},
+      {"scatter as N<=128 pieces alternating acc halves", {6, {128, 128, 128, 64, 64, 64}, {0, 128, 0, 128, 64, 64}, {0, 0, 1, 2, 2, 3}, {0, 128, 0, 0, 64, 0}, {0, 0, 1, 2, 2, 3}, it}},
+      {"concat NT=64 x2 sub-tiles: 128 128 64 64", {4, {128, 128, 64, 64}, {0, 128, 0, 128}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 2, 1, 3}, it}},
+      {"N=64 stream", {1, {64}, {0}, {0}, {0}, {0}, it}},
+      {"N=64 x2: two A, same B, two acc", {2, {64, 64}, {0, 64}, {0, 0}, {0, 0}, {0, 1}, it}},
+      {"N=64 x4: four A, same B, four acc", {4, {64, 64, 64, 64}, {0, 64, 128, 192}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 3}, it}},
+      {"N=192 stream (3 dx taps x 64)", {1, {192}, {0}, {0}, {0}, {0}, it}},
+      {"N=192 x2: two A, same B, two acc", {2, {192, 192}, {0, 256}, {0, 0}, {0, 0}, {0, 1}, it}},
+  };
+  printf("\n%-66s | %10s %11s %12s %10s\n", "pattern (operands rotate over 4 A tiles / 4 B slabs)", "ns/pattern", "cyc/pattern", "cyc/256cols", "TF/s chip");
+  for (auto& nm : ps) {
+    switch (nm.p.np) {
+      case 1: launch_pattern<1>(nm.p, sms, cyc, ns, smem); break;
+      case 2: launch_pattern<2>(nm.p, sms, cyc, ns, smem); break;
+      case 3: launch_pattern<3>(nm.p, sms, cyc, ns, smem); break;
+      case 4: launch_pattern<4>(nm.p, sms, cyc, ns, smem); break;
+      case 6: launch_pattern<6>(nm.p, sms, cyc, ns, smem); break;
+      default: continue;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("%s failed: %s\n", nm.name, cudaGetErrorString(e));
+      return;
+    }
+    std::vector<unsigned long long> hc(sms), hn(sms);
+    cudaMemcpy(hc.data(), cyc, sms * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hn.data(), ns, sms * 8, cudaMemcpyDeviceToHost);
+    double mc = 0, mn = 0;
+    for (int i = 0; i < sms; ++i) {
+      mc += hc[i];
+      mn += hn[i];
+    }
+    mc /= sms * (double)nm.p.iters;
+    mn /= sms * (double)nm.p.iters;
+    int cols = 0;
+    for (int k = 0; k < nm.p.np; ++k) cols += nm.p.n[k];
+    printf("%-66s | %10.2f %11.2f %12.2f %10.1f\n", nm.name, mn, mc, mc * 256.0 / cols, 2.0 * 128 * 16 * cols / mn * sms / 1e3);
+  }
+}
+
+int main(int argc, char** argv) {
   const int smem = 1024 + 160 * 1024;
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int sms = 0;
@@ -98,22 +250,27 @@ int main() {
   cudaMalloc(&cyc, sms * 8);
   cudaMalloc(&ns, sms * 8);
   cudaMalloc(&sink, 4);
+  if (argc > 1 && argv[1][0] == 'p') {
+    run_patterns(sms, cyc, ns, smem);
+    return 0;
+  }
   std::vector<Case> cases;
   const int iters = 20000;
-  for (int lsu = 0; lsu < 2; ++lsu) {
-    for (int n : {32, 64, 96, 128, 192, 256}) {
-      cases.push_back({n, 0, 128, 0, lsu, iters});          // dense, aligned
-      cases.push_back({n, 16, 128, 0, lsu, iters});         // dense, start + 16 B (x-shift in a dense box)
-      cases.push_back({n, 0, 288, 0, lsu, iters});          // 18-pixel halo rows (modconv_halo MT=2), aligned start
-      cases.push_back({n, 304, 288, 0, lsu, iters});        // tap (1,1) of the halo tile
-      cases.push_back({n, 0, 256, 0, lsu, iters});          // 16-pixel rows
-      cases.push_back({n, 0, 160, 0, lsu, iters});          // 10-pixel halo rows (MT=1)
+  for (int n : {64, 128, 192, 256}) {
+    for (int acc : {1, 2, 4}) {
+      if (acc * n > 512) continue;
+      for (int arot : {1, 4}) {
+        for (int brot : {1, 4}) {
+          cases.push_back({n, 0, 288, 0, 0, iters, arot, brot, acc});
+        }
+      }
     }
-    cases.push_back({128, 0, 288, 64, lsu, iters});         // concat pair: N=128 + N=64 alternating (modconv_halo NT=64)
-    cases.push_back({256, 0, 128, 128, lsu, iters});
-    cases.push_back({256, 0, 128, 64, lsu, iters});
   }
-  printf("%-5s %-6s %-6s %-4s %-4s | %10s %10s %10s\n", "N", "a_off", "a_sbo", "N2", "lsu", "ns/iter", "cyc/iter", "TF/s chip");
+  // the concat pair of modconv_halo NT=64 (N=128 then N=64 on two sub-tiles), distinct operands
+  cases.push_back({128, 0, 288, 64, 0, iters, 4, 1, 1});
+  // shared-memory pressure on the distinct-operand cases
+  for (int n : {64, 128, 256}) cases.push_back({n, 0, 288, 0, 1, iters, 4, 1, n == 256 ? 2 : 4});
+  printf("%-5s %-5s %-5s %-5s %-4s %-4s | %10s %10s %10s\n", "N", "N2", "arot", "brot", "acc", "lsu", "ns/iter", "cyc/iter", "TF/s chip");
   for (const Case& c : cases) {
     mma_rate_kernel<<<sms, 256, smem>>>(c, cyc, ns, sink);
     cudaError_t e = cudaDeviceSynchronize();
@@ -132,7 +289,7 @@ int main() {
     mc /= sms * (double)c.iters;
     mn /= sms * (double)c.iters;
     const double flop = 2.0 * 128 * 16 * (c.n + c.n2);
-    printf("%-5d %-6d %-6d %-4d %-4d | %10.2f %10.2f %10.1f\n", c.n, c.a_off, c.a_sbo, c.n2, c.lsu, mn, mc, flop / mn * sms / 1e3);
+    printf("%-5d %-5d %-5d %-5d %-4d %-4d | %10.2f %10.2f %10.1f\n", c.n, c.n2, c.a_rot, c.b_rot, c.acc_rot, c.lsu, mn, mc, flop / mn * sms / 1e3);
   }
   return 0;
 }
