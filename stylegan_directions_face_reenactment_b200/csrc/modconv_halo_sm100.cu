@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
                                                                             const ConvKernelParams p, const FusedFirParams f) {
   using Cfg = HaloCfg<NT, MT, FUSED>;
   constexpr int AS = Cfg::kAStages, BS = Cfg::kBStages;
+  constexpr bool kPacedIssue = FUSED && NT <= 128;      // see the two MMA issuers below
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* a_empty = a_full + AS;
@@ -130,6 +131,9 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
 
   const int out_tiles = p.m_tiles * p.n_tiles;
   const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice of channel blocks)
+
+  // (setmaxnreg re-dealing of the 64 K registers between the service / epilogue / producer warp groups was tried: ptxas keeps
+  //  the 128-register cap of the 512-thread launch bound in the `inc` regions and spills MORE in the `dec` region)
 
   if (FUSED && warp >= 8) {
     // ------------------------------------------------------------------ FIR producers (fused mode; ksplit == 1)
@@ -238,7 +242,138 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // The issuing thread is the critical resource: its instructions run back to back at ~8 cycles each (uniform datapath),
+    // and tcgen05.mma executes in 64 (N = 128) .. 128 (N = 256) cycles (tools/microbench/mma_rate.cu: a stream of precomputed
+    // descriptors reaches exactly that), so an MMA may cost at most ~8 issue instructions.  The first version rebuilt both
+    // shared-memory descriptors per MMA (~20 instructions: 170-180 cycles per N = 256 MMA, 100 per N = 128 MMA measured with
+    // all loads switched off).  Here: ring base descriptors once, one per stage / slab by a multiply-add, the nine taps fully
+    // unrolled so that every MMA's operands are base + compile-time constant.
+    if (lane == 0 && !kPacedIssue) {
+      const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
+      const uint32_t idesc_cat = umma_idesc(p.fmt, kTileM, Cfg::kConcat ? 2 * NT : NT);
+      constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;
+      // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64)
+      constexpr uint32_t kBLbo = Cfg::kConcat ? 2 * NT * 16 : NT * 16, kBPlane = Cfg::kConcat ? NT * 16 : NT * 64;
+      // offsets in descriptor units (16 B)
+      constexpr uint64_t kAJ = (2 * kALbo) >> 4, kALo = kAPlane >> 4, kBJ = (2 * kBLbo) >> 4, kBLo = kBPlane >> 4;
+      const uint64_t a_ring = umma_desc(smem_u32(a_base), kALbo, kASbo);
+      const uint64_t b_ring = umma_desc(smem_u32(b_base), kBLbo, 128);
+      const bool acc_always = (p.debug & 1024) != 0;
+      const uint32_t idesc_lo = (p.debug & 64) ? idesc_cat : idesc;
+      // 0: concat scheme (NT <= 64), 1: sub-tile interleaved three products (NT >= 128), 2: single pass / experiment orders
+      const int variant = p.single ? 2 : (Cfg::kConcat ? ((p.debug & 32) ? 2 : 0) : ((p.debug & 128) ? 2 : 1));
+      uint32_t ai = 0, bi = 0, tcount = 0;
+      uint32_t as = 0, aphase = 0, bs = 0, bphase = 0;          // ring slot + phase of the next stage / slab (no divisions)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (MT * Cfg::kAccCols);
+        const int ks = tile % p.ksplit;
+        const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb, ++ai) {
+          if (!(p.debug & 16) || ai < AS) mbar_wait(&a_full[as], aphase);
+          tc_fence_after();
+          const uint64_t a_d = a_ring + static_cast<uint64_t>(as) * (Cfg::kABytes >> 4);
+          const uint32_t first = (kb > kb0 || acc_always) ? 1u : 0u;      // accumulate flag of the very first MMA of the tile
+          // one kernel row (dy) per trip, its three taps unrolled: the variant in use stays a compact, contiguous piece of
+          // code (nine unrolled taps x four variants overflowed the instruction cache: the 64-channel layer ran 26 % slower)
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t a_row = a_d + static_cast<uint64_t>(dy * Cfg::kHW);
+            const uint32_t first_row = dy == 0 ? first : 1u;
+            auto slab_wait = [&]() {
+              if (!(p.debug & 4) || bi < BS) mbar_wait(&b_full[bs], bphase);
+              tc_fence_after();
+              return b_ring + static_cast<uint64_t>(bs) * (Cfg::kBBytes >> 4);
+            };
+            auto slab_done = [&]() {
+              if (!(p.debug & 256)) umma_commit(&b_empty[bs]);     // weight slab consumed (experiment 256 with 4|16: no ring commits)
+              ++bi;
+              if (++bs == BS) {
+                bs = 0;
+                bphase ^= 1;
+              }
+            };
+            if (variant == 0) {
+              // NT <= 64: A_hi x [W_hi | W_lo] (N = 2 NT) for both sub-tiles, then A_lo x W_hi (N = NT): MMAs of one shape are
+              // issued together — alternating the two shapes on the same accumulator columns costs ~25 ns per switch
+              // (0.64 -> 0.52 ms on the 64 -> 64 layer at 256^2; debug 32 = the old alternating order)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t b_d = slab_wait(), a_t = a_row + dx;
+#pragma unroll
+                for (int j = 0; j < kBlockK / 16; ++j)
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt)
+                    umma_bf16(d_tmem + mt * Cfg::kAccCols, a_t + (mt * 8 + j * kAJ), b_d + j * kBJ, idesc_cat,
+                              (dx | j) != 0 ? 1u : first_row);                                 // hi*hi | hi*lo
+#pragma unroll
+                for (int j = 0; j < kBlockK / 16; ++j)
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt)
+                    umma_bf16(d_tmem + mt * Cfg::kAccCols, a_t + (mt * 8 + j * kAJ + kALo), b_d + j * kBJ, idesc_lo, 1);   // lo*hi
+                slab_done();
+              }
+            } else if (variant == 1) {
+              // NT >= 128: consecutive MMAs alternate between the sub-tiles' accumulators (MT = 2): an MMA that accumulates
+              // into the TMEM columns of its predecessor waits for it; debug 128 = three products of a sub-tile back to back
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t b_d = slab_wait(), a_t = a_row + dx;
+#pragma unroll
+                for (int j = 0; j < kBlockK / 16; ++j)
+#pragma unroll
+                  for (int prod = 0; prod < 3; ++prod)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                      umma_bf16(d_tmem + mt * NT, a_t + (mt * 8 + j * kAJ + (prod == 0 ? kALo : 0)),
+                                b_d + (j * kBJ + (prod == 1 ? kBLo : 0)), idesc,
+                                (dx | j | prod) != 0 ? 1u : first_row);                        // lo*hi, hi*lo, hi*hi
+                slab_done();
+              }
+            } else {
+              // single-pass mode and the experiment orders
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t b_d = slab_wait(), a_t = a_row + dx;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int j = 0; j < kBlockK / 16; ++j) {
+                    const uint64_t a_hi = a_t + (mt * 8 + j * kAJ), a_lo = a_hi + kALo;
+                    const uint64_t b_hi = b_d + j * kBJ;
+                    const uint32_t acc0 = (dx | j) != 0 ? 1u : first_row;
+                    if (p.single) {
+                      umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc, acc0);
+                    } else if (Cfg::kConcat) {
+                      umma_bf16(d_tmem + mt * Cfg::kAccCols, a_hi, b_hi, idesc_cat, acc0);     // hi*hi | hi*lo
+                      umma_bf16(d_tmem + mt * Cfg::kAccCols, a_lo, b_hi, idesc_lo, 1);         // lo*hi (64: + lo*lo)
+                    } else {
+                      umma_bf16(d_tmem + mt * NT, a_lo, b_hi, idesc, acc0);
+                      umma_bf16(d_tmem + mt * NT, a_hi, b_hi + kBLo, idesc, 1);
+                      umma_bf16(d_tmem + mt * NT, a_hi, b_hi, idesc, 1);
+                    }
+                  }
+                }
+                slab_done();
+              }
+            }
+          }
+          if (!(p.debug & 256)) umma_commit(&a_empty[as]);       // halo block consumed by all nine taps
+          if (++as == AS) {
+            as = 0;
+            aphase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);          // accumulators complete
+      }
+    }
+    // ---- paced issuer (FUSED, NT <= 128): descriptors rebuilt per MMA, taps not unrolled.  The fused low-channel kernels are
+    // bound by shared-memory bandwidth (MMA operand reads + FIR producers ~0.85 wavefronts / cycle); measured on the same B200,
+    // the streamlined issuer above makes them SLOWER (64 -> 64 @ 256^2: 0.69 -> 0.80 ms, 128 -> 128 @ 128^2: 0.49 -> 0.50 ms):
+    // bursts of operand reads starve the producer warps.  Everywhere else it wins (512 -> 512 @ 32^2: 0.40 -> 0.36 ms).
+    if (lane == 0 && kPacedIssue) {
       const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
       const uint32_t idesc_cat = umma_idesc(p.fmt, kTileM, Cfg::kConcat ? 2 * NT : NT);
       constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;

@@ -32,7 +32,7 @@ struct ScatterCfg {
   static constexpr int kBSlabs = kGroups * 4;
   static constexpr int kAStages = 4;                                      // one slot per shift: slot index == shift
   static constexpr int kHaloStages = 3;                                   // wrapped-halo tiles: ring of channel blocks in the same 64 KiB
-  static constexpr int kHaloStageBytes = 21760;                           // >= 8 chunk-planes x (129 + 32) entries x 16 B, 128-aligned
+  static constexpr int kHaloStageBytes = 8 * 144 * 16 + 2304;             // 8 chunk-planes of <= 144 box entries + the over-read of the last one
   static constexpr int kStageOff = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
   static constexpr int kSmemBytes = kStageOff + 8 * kTileM * 16;          // + epilogue staging: 8 channel groups x 128 pixels x 16 B
   static_assert(kSmemBytes <= 227 * 1024, "shared memory");
@@ -44,11 +44,13 @@ __device__ __forceinline__ int scatter_prefix(int nt, int sft) {                
   return sft == 0 ? 0 : (sft == 1 ? nt : (sft == 2 ? nt + nt / 2 : 2 * nt));
 }
 
-template <int NT>
+template <int NT, int HE>      // HE: box entries per chunk-plane of the wrapped-halo tiles (144 or 140), 0 = dense-box tiles
 __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap tmap_out,
                                                                 const ConvKernelParams p) {
   using Cfg = ScatterCfg<NT>;
+  constexpr bool HALO = HE != 0;
+  constexpr int kHE = HE != 0 ? HE : 144;
   constexpr int AS = Cfg::kAStages, BSL = Cfg::kBSlabs;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * (p.single ? 64u : 128u);   // single pass: hi plane only
-      const uint32_t halo_bytes = static_cast<uint32_t>(p.bw * (p.bh + 1)) * (p.single ? 64u : 128u);
+      const uint32_t halo_bytes = static_cast<uint32_t>(kHE) * (p.single ? 64u : 128u);      // box = bw x box_rows entries
       const uint32_t b_row = p.single ? 64u : 128u;                                       // slabs are plane-major: hi half first
       uint32_t g = 0;                                  // running channel-block counter: ring slots and phases
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const uint32_t grp = g % Cfg::kGroups;
           const uint32_t a_par = (g & 1) ^ 1, b_par = ((g / Cfg::kGroups) & 1) ^ 1;
           uint8_t* bdst = b_base + grp * Cfg::kGroupBytes;
-          if (p.halo) {              // one box per channel block: tile + top row / left column halo, all four shifts read it
+          if (HALO && !((p.debug & 16) && g >= Cfg::kHaloStages)) {   // one box per channel block: tile + top row / left column halo
             const uint32_t hs = g % Cfg::kHaloStages;
             mbar_wait(&a_empty[hs], ((g / Cfg::kHaloStages) & 1) ^ 1);
             mbar_expect_tx(&a_full[hs], halo_bytes);
@@ -124,11 +126,12 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           for (int sft = 0; sft < 4; ++sft) {
             const int n_s = scatter_rows(NT, sft), prefix = scatter_prefix(NT, sft);
             const uint32_t bs = grp * 4 + sft;
-            if (!p.halo) {
+            if (!HALO) {
               mbar_wait(&a_empty[sft], a_par);
               mbar_expect_tx(&a_full[sft], a_bytes);
               tma_load_5d(a_base + sft * kABytes, &tmap, &a_full[sft], (x0 - (sft & 1)) * 8, y0 - (sft >> 1), b0, kc * 4, 0);
             }
+            if ((p.debug & 4) && g >= Cfg::kGroups) continue;          // experiment 4: weight ring loaded once
             mbar_wait(&b_empty[bs], b_par);
             mbar_expect_tx(&b_full[bs], n_s * b_row);
             bulk_g2s(bdst + prefix * 128, wkc + prefix * 128, n_s * b_row, &b_full[bs]);
@@ -138,57 +141,93 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
+    // The issuing thread is the critical resource (see modconv_halo_sm100.cu): ~8 cycles per instruction against 48 .. 128 cycles
+    // per MMA.  Ring base descriptors are built once; per channel block one multiply-add per ring, per shift one add, and
+    // every MMA's operands are base + compile-time constant (wrapped-halo tiles have a FIXED chunk stride of kHaloEntries
+    // box entries for that; the dense-box tiles keep run-time strides).
     if (lane == 0) {
-      // descriptors = base (LBO/SBO/version fields + ring base address) + byte offset >> 4
-      const uint32_t a_lbo = static_cast<uint32_t>(p.halo ? p.bw * (p.bh + 1) : p.rows) * 16;      // bytes per chunk-plane of a box
-      const uint64_t a_desc0 = umma_desc(smem_u32(a_base), a_lbo, 128);
+      const uint32_t a_lbo = HALO ? kHE * 16u : static_cast<uint32_t>(p.rows) * 16u;   // bytes per chunk-plane of a box
+      const uint64_t a_ring = umma_desc(smem_u32(a_base), a_lbo, 128);
       // wrapped-halo tiles: M row r of shift (a, b) = box entry bw + 1 + r - (a * bw + b)
       const uint64_t h_off[4] = {static_cast<uint64_t>(p.bw + 1), static_cast<uint64_t>(p.bw), 1, 0};
       const uint64_t a_lo_off = (a_lbo * 4) >> 4, a_j_off = (a_lbo * 2) >> 4;
-      uint64_t b_desc0[4];
+      constexpr uint64_t kHLo = (kHE * 16 * 4) >> 4, kHJ = (kHE * 16 * 2) >> 4;
+      uint64_t b_ring[4];
       uint32_t idesc[4];
 #pragma unroll
       for (int sft = 0; sft < 4; ++sft) {
         const uint32_t n_s = scatter_rows(NT, sft);
-        b_desc0[sft] = umma_desc(smem_u32(b_base) + scatter_prefix(NT, sft) * 128, n_s * 16, 128);
+        b_ring[sft] = umma_desc(smem_u32(b_base) + scatter_prefix(NT, sft) * 128, n_s * 16, 128);
         idesc[sft] = umma_idesc(p.fmt, kTileM, static_cast<int>(n_s));
       }
       uint32_t g = 0, tcount = 0;
+      uint32_t hs = 0, hphase = 0, grp = 0, gphase = 0;      // ring slot + phase of the next halo stage / weight group
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * NT;
         for (int kc = 0; kc < p.kchunks; ++kc, ++g) {
-          const uint32_t grp = g % Cfg::kGroups;
-          const uint32_t a_par = g & 1, b_par = (g / Cfg::kGroups) & 1;
-          const uint64_t grp_off = (grp * Cfg::kGroupBytes) >> 4;
+          const uint32_t a_par = g & 1;
+          const uint64_t grp_off = static_cast<uint64_t>(grp) * (Cfg::kGroupBytes >> 4);
+          const bool b_skip = (p.debug & 4) && g >= Cfg::kGroups;
+          const uint32_t acc0 = kc != 0 ? 1u : 0u;
+          if (HALO && !p.single) {
+            if (!((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
+            const uint64_t a_st = a_ring + static_cast<uint64_t>(hs) * (Cfg::kHaloStageBytes >> 4);
 #pragma unroll
-          for (int sft = 0; sft < 4; ++sft) {
-            const uint32_t n_s = scatter_rows(NT, sft);
-            const uint32_t coloff = sft >= 2 ? NT / 4 : 0;        // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
-            if (!p.halo) mbar_wait(&a_full[sft], a_par);
-            else if (sft == 0) mbar_wait(&a_full[g % Cfg::kHaloStages], (g / Cfg::kHaloStages) & 1);
-            mbar_wait(&b_full[grp * 4 + sft], b_par);
-            tc_fence_after();
-            const uint64_t a_hi0 = p.halo ? a_desc0 + (((g % Cfg::kHaloStages) * Cfg::kHaloStageBytes) >> 4) + h_off[sft]
-                                          : a_desc0 + ((sft * kABytes) >> 4);
-            const uint64_t b_hi0 = b_desc0[sft] + grp_off;
+            for (int sft = 0; sft < 4; ++sft) {
+              constexpr uint32_t kCol[4] = {0, 0, NT / 4, NT / 4};          // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
+              const uint32_t n_s = scatter_rows(NT, sft);
+              if (!b_skip) mbar_wait(&b_full[grp * 4 + sft], gphase);
+              tc_fence_after();
+              const uint64_t a_s = a_st + h_off[sft], b_s = b_ring[sft] + grp_off;
 #pragma unroll
-            for (int j = 0; j < kBlockK / 16; ++j) {
-              const uint64_t a_hi = a_hi0 + j * a_j_off, a_lo = a_hi + a_lo_off;
-              const uint64_t b_hi = b_hi0 + j * ((n_s * 32) >> 4), b_lo = b_hi + ((n_s * 64) >> 4);
-              if (!p.single) {
-                umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc[sft], (kc | sft | j) != 0);
-                umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc[sft], 1);
-                umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], 1);
-              } else {
-                umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], (kc | sft | j) != 0);
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint64_t bj = static_cast<uint64_t>(j) * ((n_s * 32) >> 4), blo = (n_s * 64) >> 4;
+                umma_bf16(d_tmem + kCol[sft], a_s + (j * kHJ + kHLo), b_s + bj, idesc[sft], (sft | j) != 0 ? 1u : acc0);
+                umma_bf16(d_tmem + kCol[sft], a_s + j * kHJ, b_s + (bj + blo), idesc[sft], 1);
+                umma_bf16(d_tmem + kCol[sft], a_s + j * kHJ, b_s + bj, idesc[sft], 1);
               }
+              if (sft == 3) umma_commit(&a_empty[hs]);
+              umma_commit(&b_empty[grp * 4 + sft]);
             }
-            if (!p.halo) umma_commit(&a_empty[sft]);
-            else if (sft == 3) umma_commit(&a_empty[g % Cfg::kHaloStages]);
-            umma_commit(&b_empty[grp * 4 + sft]);
+          } else {
+#pragma unroll
+            for (int sft = 0; sft < 4; ++sft) {
+              const uint32_t n_s = scatter_rows(NT, sft);
+              const uint32_t coloff = sft >= 2 ? NT / 4 : 0;
+              if (!HALO) mbar_wait(&a_full[sft], a_par);
+              else if (sft == 0 && !((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
+              if (!b_skip) mbar_wait(&b_full[grp * 4 + sft], gphase);
+              tc_fence_after();
+              const uint64_t a_hi0 = HALO ? a_ring + static_cast<uint64_t>(hs) * (Cfg::kHaloStageBytes >> 4) + h_off[sft]
+                                            : a_ring + ((sft * kABytes) >> 4);
+              const uint64_t b_hi0 = b_ring[sft] + grp_off;
+#pragma unroll
+              for (int j = 0; j < kBlockK / 16; ++j) {
+                const uint64_t a_hi = a_hi0 + j * a_j_off, a_lo = a_hi + a_lo_off;
+                const uint64_t b_hi = b_hi0 + j * ((n_s * 32) >> 4), b_lo = b_hi + ((n_s * 64) >> 4);
+                if (!p.single) {
+                  umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc[sft], (sft | j) != 0 ? 1u : acc0);
+                  umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc[sft], 1);
+                  umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], 1);
+                } else {
+                  umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc[sft], (sft | j) != 0 ? 1u : acc0);
+                }
+              }
+              if (!HALO) umma_commit(&a_empty[sft]);
+              else if (sft == 3) umma_commit(&a_empty[hs]);
+              umma_commit(&b_empty[grp * 4 + sft]);
+            }
+          }
+          if (HALO && ++hs == Cfg::kHaloStages) {
+            hs = 0;
+            hphase ^= 1;
+          }
+          if (++grp == Cfg::kGroups) {
+            grp = 0;
+            gphase ^= 1;
           }
         }
         umma_commit(&tfull[acc]);
@@ -203,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     int bl = r / (p.bw * p.bh);
     int slot = r;                                      // position inside the staged / stored box; < 0: nothing to store
     int sx = p.bw, sy = p.bh;                          // tile stride on the grid
-    if (p.halo) {                                      // box entry bw + 1 + r: column 0 of the box is halo (garbage rows)
+    if (HALO) {                                      // box entry bw + 1 + r: column 0 of the box is halo (garbage rows)
       const int e = p.bw + 1 + r;
       xx = e % p.bw - 1;
       yy = e / p.bw - 1;
@@ -302,8 +341,12 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
   using Cfg = ScatterCfg<NT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(upconv_scatter_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 144>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 140>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("upconv_scatter: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return 1;
@@ -317,7 +360,17 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
   CUtensorMap tmap_out = tmap;
   q.tma_store = (!tma_off && p.bb == 1 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;
   if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
-  upconv_scatter_kernel<NT><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+  const int he = p.halo ? p.bw * p.box_rows : 0;
+  if (he == 144)
+    upconv_scatter_kernel<NT, 144><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+  else if (he == 140)
+    upconv_scatter_kernel<NT, 140><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+  else if (he == 0)
+    upconv_scatter_kernel<NT, 0><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+  else {
+    set_error("upconv_scatter: unsupported halo box of %d entries", he);
+    return 1;
+  }
   count_launch();
   return check_launch("upconv_scatter_kernel") ? 0 : 1;
 }

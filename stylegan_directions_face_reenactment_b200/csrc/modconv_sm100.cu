@@ -129,8 +129,17 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       // A stage image: [plane][chunk][row][8] with `rows` dense rows per chunk (the TMA box), rows <= 128
-      const uint32_t a_lbo = static_cast<uint32_t>(p.rows) * 16, a_plane = a_lbo * 4;
-      uint32_t it = 0, tcount = 0;
+      // (issuing thread = critical resource, see modconv_halo_sm100.cu: stage base descriptors by one multiply-add, the six
+      //  MMAs of a stage at base + loop-invariant offsets)
+      const uint32_t a_lbo = static_cast<uint32_t>(p.rows) * 16;
+      const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
+      // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64, see pack_weight_kernel)
+      constexpr uint32_t b_lbo = NT <= 64 ? 2 * NT * 16 : NT * 16, b_plane = NT <= 64 ? NT * 16 : NT * 64;
+      const uint64_t a_ring = umma_desc(smem_u32(stage_base), a_lbo, 128);
+      const uint64_t b_ring = umma_desc(smem_u32(stage_base) + kABytes, b_lbo, 128);
+      const uint64_t a_j = (2 * a_lbo) >> 4, a_lo_off = (4 * a_lbo) >> 4;
+      constexpr uint64_t b_j = (2 * b_lbo) >> 4, b_lo_off = b_plane >> 4;
+      uint32_t it = 0, tcount = 0, s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
@@ -139,31 +148,28 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
         const int ks = tile % p.ksplit;
         const int k0 = ks * k_iters / p.ksplit, k1 = (ks + 1) * k_iters / p.ksplit;
         for (int k = k0; k < k1; ++k, ++it) {
-          constexpr uint32_t coloff = 0;
-          const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
-          // weight slab: [plane][chunk][n][8] (NT > 64) or [chunk][plane][n][8] (NT <= 64, see pack_weight_kernel)
-          constexpr uint32_t b_lbo = NT <= 64 ? 2 * NT * 16 : NT * 16, b_plane = NT <= 64 ? NT * 16 : NT * 64;
-          const uint32_t s = it % S;
-          const uint32_t ph = (it / S) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + s * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t st = static_cast<uint64_t>(s) * (Cfg::kStageBytes >> 4);
+          const uint64_t a_s = a_ring + st, b_s = b_ring + st;
+          const uint32_t acc0 = k > k0 ? 1u : 0u;
 #pragma unroll
           for (int j = 0; j < kBlockK / 16; ++j) {
-            const uint64_t a_hi = umma_desc(a_addr + j * 2 * a_lbo, a_lbo, 128);
-            const uint64_t a_lo = umma_desc(a_addr + a_plane + j * 2 * a_lbo, a_lbo, 128);
-            const uint64_t b_hi = umma_desc(b_addr + j * 2 * b_lbo, b_lbo, 128);
-            const uint64_t b_lo = umma_desc(b_addr + b_plane + j * 2 * b_lbo, b_lbo, 128);
+            const uint64_t a_hi = a_s + j * a_j, a_lo = a_hi + a_lo_off;
+            const uint64_t b_hi = b_s + j * b_j, b_lo = b_hi + b_lo_off;
             if (!p.single) {
-              umma_bf16(d_tmem + coloff, a_lo, b_hi, idesc, k > k0 || j != 0);
-              umma_bf16(d_tmem + coloff, a_hi, b_lo, idesc, 1);
-              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, 1);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, j != 0 ? 1u : acc0);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
             } else {
-              umma_bf16(d_tmem + coloff, a_hi, b_hi, idesc, k > k0 || j != 0);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, j != 0 ? 1u : acc0);
             }
           }
           umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+          if (++s == S) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         umma_commit(&tfull[as]);       // accumulator complete
       }
@@ -454,20 +460,27 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
       }
     }
     p->halo = 0;
+    p->box_rows = 0;
     static const bool halo_off = [] { const char* e = getenv("SGR_UP_HALO"); return e && e[0] == '0'; }();
     if (!halo_off && p->bb == 1 && !getenv("SGR_UP_BOX")) {
       // Wrapped-halo tiles: one dense box of hbw x (vr + 1) pixels starting one pixel up / left of the tile; M row r reads box
       // entry hbw + 1 + r - (a * hbw + b) for shift (a, b), so the entries of box column 0 produce garbage (their left
       // neighbour wraps to the previous row) and are discarded: hbw - 1 valid columns x vr valid rows, vr * hbw <= 129.
       // A traffic L2 -> shared memory drops from 4 boxes per channel block to 1.1 (the kernel was bound by exactly that).
+      // The box has 144 or 140 entries (hbw x rows): a fixed chunk stride makes every MMA operand of the kernel base +
+      // compile-time constant (the issuing thread is the critical resource); one kernel instantiation per entry count.
       long long best = -1;
-      int best_w = 0;
-      for (int hbw = std::min(32, p->W + 1); hbw >= 9; --hbw) {
-        const int vr = 129 / hbw;
+      int best_w = 0, best_vr = 0, best_rows = 0;
+      static const int shapes[6][2] = {{24, 6}, {18, 8}, {16, 9}, {14, 10}, {12, 12}, {9, 16}};
+      for (const auto& sh : shapes) {
+        const int hbw = sh[0];
+        const int vr = std::min(sh[1] - 1, 129 / hbw);
         const long long tiles = static_cast<long long>((p->W + hbw - 2) / (hbw - 1)) * ((p->H + vr - 1) / vr);
         if (best < 0 || tiles < best) {
           best = tiles;
           best_w = hbw;
+          best_vr = vr;
+          best_rows = sh[1];
         }
       }
       // measured (tools/gpu_layer_bench.py, B=32): 129^2 grid 150 vs 143 tiles -5 %, 65^2 39 vs 42 -1 %, 33^2 10 vs 9 +6 %:
@@ -476,12 +489,14 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
       if (best_w > 0 && best * 100 <= legacy * 106) {
         p->halo = 1;
         p->bw = best_w;
-        p->bh = 129 / best_w;
+        p->bh = best_vr;                // valid rows = tile stride in y
+        p->box_rows = best_rows;        // rows of the TMA box
         p->bb = 1;
       }
     }
   } else {
     p->halo = 0;
+    p->box_rows = 0;
     p->H = a->h_in;
     p->W = a->w_in;
     tile_box(a->h_in, a->w_in, &p->bw, &p->bh, &p->bb);

@@ -272,7 +272,7 @@ static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* 
     if (make_act_tensor_map(&tmap, args->x_c8, args->batch, 4 * args->cin, args->h_in + 1, args->w_in + 1, p.bw, p.bh, p.bb,
                             p.single ? 1 : 2))
       return 1;
-  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.bh + (p.halo ? 1 : 0),
+  } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.halo ? p.box_rows : p.bh,
                                  p.bb, p.single ? 1 : 2)) {
     return 1;
   }

@@ -81,6 +81,7 @@ struct ConvKernelParams {
   // scatter up-conv, wrapped-halo tiles (modconv_scatter_sm100.cu): ONE dense TMA box of bw x (bh + 1) pixels per channel block
   // whose first row / column are the halo; the four shifts are descriptor offsets into it.  bw - 1 valid columns, bh valid rows.
   int halo;
+  int box_rows;                 // rows of that TMA box (bw * box_rows = 144 or 140 entries: fixed chunk strides in the kernel)
 };
 
 // FIR pass of the preceding scatter up-conv folded into a halo convolution's producer warps (fir_producer.cuh)

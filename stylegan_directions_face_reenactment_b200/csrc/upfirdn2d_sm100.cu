@@ -97,15 +97,14 @@ __global__ void upfirdn2d_kernel(const float* __restrict__ x, float* __restrict_
 // up == down == 1 with a 4x4 FIR (the Blur after an up-conv, model.py:72-88; the mode that moves the most bytes): row-walking
 // variant.  A thread owns VX = 4 adjacent output columns and walks ROWS output rows downwards with a 4-row register window,
 // so every input element is loaded ONCE (the kernel above re-reads each input row for its four output rows and re-does the
-// halo shuffles: ~30 instructions per output, issue-bound at 27 % of the HBM rate); per output row: 4 loads (issued PF rows
-// ahead: the walk is a dependent chain, without the prefetch the kernel is latency-bound), 3 halo shuffles from the lane to
-// the right, the FMAs and one 16-byte store.  When the taps are an outer product gy (x) gx (checked in the kernel; always the
+// halo shuffles: ~30 instructions per output, issue-bound at 27 % of the HBM rate); per output row: 4 loads, 3 halo shuffles from the
+// lane to the right, the FMAs and one 16-byte store.  When the taps are an outer product gy (x) gx (checked in the kernel; always the
 // case for make_kernel's FIRs) the FIR runs separably: horizontal pass on the incoming row (4 FMAs / output), vertical
 // pass over the window of row results (4 FMAs / output) instead of 16.
 template <bool SEP, int ROWS>
 __device__ __forceinline__ void upfirdn2d_rows_body(const float* __restrict__ x, float* __restrict__ y, const float* sk, int planes,
                                                     int in_h, int in_w, int out_h, int out_w, int pad0) {
-  constexpr int VX = 4, K = 4, PF = 3;
+  constexpr int VX = 4, K = 4;
   const int lane = threadIdx.x & 31;
   const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * VX;
   const int oy0 = (blockIdx.y * blockDim.y + threadIdx.y) * ROWS;
@@ -121,86 +120,75 @@ __device__ __forceinline__ void upfirdn2d_rows_body(const float* __restrict__ x,
     for (int j = 0; j < K; ++j) t2[i][j] = SEP ? 0.f : sk[i * K + j];
   }
   const int rows = min(ROWS, out_h - oy0);
-  const int n_in = rows + K - 1;                             // input rows oy0 - pad0 .. oy0 + rows + K - 2 - pad0
   for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
     const float* xp = x + static_cast<size_t>(pl) * in_h * in_w;
     float* yp = y + static_cast<size_t>(pl) * out_h * out_w;
-    // raw row r: the lane's VX values + (lane 31 only) the K-1 values right of them
-    auto load_row = [&](int r, float (&own)[VX], float (&edge)[K - 1]) {
-      const int iy = oy0 + r - pad0;
-      const bool row_ok = r < n_in && iy >= 0 && iy < in_h;  // warp-uniform
-#pragma unroll
-      for (int v = 0; v < VX; ++v) {
-        const int ix = ox0 + v - pad0;
-        own[v] = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
-      }
-#pragma unroll
-      for (int h = 0; h < K - 1; ++h) {
-        const int ix = ox0 + VX + h - pad0;
-        edge[h] = (lane == 31 && row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
-      }
-    };
-    float q_own[PF][VX], q_edge[PF][K - 1];
-#pragma unroll
-    for (int i = 0; i < PF; ++i) load_row(i, q_own[i], q_edge[i]);
     // window of the last K rows: SEP keeps horizontally filtered rows (VX values), otherwise raw rows (VX + K - 1 values)
     float win[K][SEP ? VX : VX + K - 1];
 #pragma unroll
     for (int i = 0; i < K; ++i)
 #pragma unroll
       for (int j = 0; j < (SEP ? VX : VX + K - 1); ++j) win[i][j] = 0.f;
-#pragma unroll 1
-    for (int r0 = 0; r0 < n_in; r0 += PF) {
+    // input rows oy0 - pad0 .. oy0 + rows + K - 2 - pad0; output row oy is complete once input row oy + K - 1 - pad0 is in.
+    // (unroll 2: the loads of the next row are independent of this row's arithmetic and get hoisted above it; an explicit
+    //  three-row prefetch queue cost 120 registers and ran 1.5x slower)
+#pragma unroll 2
+    for (int r = 0; r < rows + K - 1; ++r) {
+      const int iy = oy0 + r - pad0;
+      const bool row_ok = iy >= 0 && iy < in_h;            // warp-uniform
+      float own[VX];
 #pragma unroll
-      for (int s = 0; s < PF; ++s) {
-        const int r = r0 + s;
-        float raw[VX + K - 1];
+      for (int v = 0; v < VX; ++v) {
+        const int ix = ox0 + v - pad0;
+        own[v] = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
+      }
+      float raw[VX + K - 1];
 #pragma unroll
-        for (int v = 0; v < VX; ++v) raw[v] = q_own[s][v];
+      for (int v = 0; v < VX; ++v) raw[v] = own[v];
 #pragma unroll
-        for (int h = 0; h < K - 1; ++h) {                   // halo: the first K-1 values of the lane to the right
-          const float nb = __shfl_down_sync(0xffffffffu, q_own[s][h], 1);
-          raw[VX + h] = lane == 31 ? q_edge[s][h] : nb;
+      for (int h = 0; h < K - 1; ++h) {                     // halo: the first K-1 values of the lane to the right
+        float nb = __shfl_down_sync(0xffffffffu, own[h], 1);
+        if (lane == 31) {
+          const int ix = ox0 + VX + h - pad0;
+          nb = (row_ok && ix >= 0 && ix < in_w) ? __ldg(xp + static_cast<size_t>(iy) * in_w + ix) : 0.f;
         }
-        load_row(r + PF, q_own[s], q_edge[s]);              // refill the slot: PF rows in flight
-        if (r < n_in) {
+        raw[VX + h] = nb;
+      }
 #pragma unroll
-          for (int i = 0; i < K - 1; ++i)
+      for (int i = 0; i < K - 1; ++i)
 #pragma unroll
-            for (int j = 0; j < (SEP ? VX : VX + K - 1); ++j) win[i][j] = win[i + 1][j];
+        for (int j = 0; j < (SEP ? VX : VX + K - 1); ++j) win[i][j] = win[i + 1][j];
+      if (SEP) {
+#pragma unroll
+        for (int v = 0; v < VX; ++v)
+          win[K - 1][v] = fmaf(gx[3], raw[v + 3], fmaf(gx[2], raw[v + 2], fmaf(gx[1], raw[v + 1], gx[0] * raw[v])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < VX + K - 1; ++j) win[K - 1][j] = raw[j];
+      }
+      if (r >= K - 1 && col_ok) {
+        const int oy = oy0 + r - (K - 1);
+        float acc[VX];
+#pragma unroll
+        for (int v = 0; v < VX; ++v) {
           if (SEP) {
-#pragma unroll
-            for (int v = 0; v < VX; ++v)
-              win[K - 1][v] = fmaf(gx[3], raw[v + 3], fmaf(gx[2], raw[v + 2], fmaf(gx[1], raw[v + 1], gx[0] * raw[v])));
+            acc[v] = fmaf(gy[3], win[3][v], fmaf(gy[2], win[2][v], fmaf(gy[1], win[1][v], gy[0] * win[0][v])));
           } else {
+            float a = 0.f;
 #pragma unroll
-            for (int j = 0; j < VX + K - 1; ++j) win[K - 1][j] = raw[j];
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx) a = fmaf(t2[ky][kx], win[ky][v + kx], a);
+            acc[v] = a;
           }
-          if (r >= K - 1 && col_ok) {
-            const int oy = oy0 + r - (K - 1);
-            float acc[VX];
+        }
+        float* dst = yp + static_cast<size_t>(oy) * out_w + ox0;
+        if (vec_ok) {
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
 #pragma unroll
-            for (int v = 0; v < VX; ++v) {
-              if (SEP) {
-                acc[v] = fmaf(gy[3], win[3][v], fmaf(gy[2], win[2][v], fmaf(gy[1], win[1][v], gy[0] * win[0][v])));
-              } else {
-                float a = 0.f;
-#pragma unroll
-                for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-                  for (int kx = 0; kx < K; ++kx) a = fmaf(t2[ky][kx], win[ky][v + kx], a);
-                acc[v] = a;
-              }
-            }
-            float* dst = yp + static_cast<size_t>(oy) * out_w + ox0;
-            if (vec_ok) {
-              *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            } else {
-#pragma unroll
-              for (int v = 0; v < VX; ++v)
-                if (ox0 + v < out_w) dst[v] = acc[v];
-            }
-          }
+          for (int v = 0; v < VX; ++v)
+            if (ox0 + v < out_w) dst[v] = acc[v];
         }
       }
     }

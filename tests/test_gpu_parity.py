@@ -760,7 +760,8 @@ def test_generator_parameter_gradients_train_mode(pkg, size, cm, batch):
     (G([wg], input_is_latent=True)[0] * r.cuda()).sum().backward()
     for n, p in G.named_parameters():
         if n in native:
-            assert p.grad is not None and torch.equal(p.grad, native[n]), n        # same kernels as train() mode: bit-identical
+            assert p.grad is not None, n                                            # same kernels as train() mode (block sums
+            assert torch.allclose(p.grad, native[n], rtol=1e-4, atol=1e-6 * float(native[n].abs().max())), n   # land in any order)
     # ... a constant latent in eval() mode forms them as well (backward() could be for nothing else) ...
     G.param_grads = 'auto'
     G.zero_grad(set_to_none=True)

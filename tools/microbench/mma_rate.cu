@@ -108,6 +108,8 @@ struct Pattern {
   int np;
   int n[8], col[8], bslab[8], brow[8], aidx[8];
   int iters;
+  int a_lbo, a_sbo, b_lbo, rot, a_off;      // operand layouts (0 = defaults 8192 / 256 / 8192 / 4 / 0)
+  int rand;                                 // 1: operands = pseudo-random bf16 in (-2, 2) (data-dependent switching power), 0: all 2^-7
 };
 
 template <int NP>
@@ -118,7 +120,15 @@ __global__ void __launch_bounds__(256, 1) mma_pattern_kernel(Pattern c, unsigned
   uint8_t* a_base = smem + 1024;                 // 4 A tiles x (2 k-slices x 8 KiB) = 64 KiB
   uint8_t* b_base = a_base + 64 * 1024;          // 4 B slabs x (2 k-slices x 8 KiB) = 64 KiB (N <= 512 rows per slice)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_base)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (128 * 1024) / 4; i += blockDim.x) {
+    uint32_t v = 0x3c003c00u;
+    if (c.rand) {                              // two bf16 with random sign / mantissa, exponents 2^-2 .. 2^0
+      uint32_t h = (i + 1u) * 2654435761u + blockIdx.x * 40503u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      v = (h & 0x80ff80ffu) | 0x3e003e00u | ((h >> 3) & 0x01000100u);
+    }
+    reinterpret_cast<uint32_t*>(a_base)[i] = v;
+  }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -142,8 +152,9 @@ __global__ void __launch_bounds__(256, 1) mma_pattern_kernel(Pattern c, unsigned
       tm[k] = tmem + c.col[k];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        ad[r][k] = umma_desc(smem_u32(a_base) + ((c.aidx[k] + r) & 3) * 16384, 8192, 256);        // 16-pixel rows (dense 256 B pitch)
-        bd[r][k] = umma_desc(smem_u32(b_base) + ((c.bslab[k] + r) & 3) * 16384 + c.brow[k] * 16, 8192, 128);
+        const int rr = c.rot == 1 ? 0 : r;
+        ad[r][k] = umma_desc(smem_u32(a_base) + ((c.aidx[k] + rr) & 3) * 16384 + c.a_off, c.a_lbo ? c.a_lbo : 8192, c.a_sbo ? c.a_sbo : 256);
+        bd[r][k] = umma_desc(smem_u32(b_base) + ((c.bslab[k] + rr) & 3) * 16384 + c.brow[k] * 16, c.b_lbo ? c.b_lbo : 8192, 128);
       }
     }
     unsigned long long t0, t1, n0, n1;
@@ -179,6 +190,69 @@ template <int NP>
 static void launch_pattern(const Pattern& p, int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
   cudaFuncSetAttribute(mma_pattern_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   mma_pattern_kernel<NP><<<sms, 256, smem>>>(p, cyc, ns);
+}
+
+static double time_pattern(const Pattern& p, int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
+  switch (p.np) {
+    case 1: launch_pattern<1>(p, sms, cyc, ns, smem); break;
+    case 2: launch_pattern<2>(p, sms, cyc, ns, smem); break;
+    case 3: launch_pattern<3>(p, sms, cyc, ns, smem); break;
+    default: return -1;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  std::vector<unsigned long long> hc(sms);
+  cudaMemcpy(hc.data(), cyc, sms * 8, cudaMemcpyDeviceToHost);
+  double mc = 0;
+  for (int i = 0; i < sms; ++i) mc += hc[i];
+  return mc / (sms * (double)p.iters);
+}
+
+// which operand layout property costs the N=256 MMA 171 instead of 128 cycles?
+static void run_layout_sweep(int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
+  printf("\n%-5s %-7s %-6s %-6s %-6s %-4s | %10s\n", "N", "a_lbo", "a_sbo", "a_off", "b_lbo", "rot", "cyc/MMA");
+  for (int n : {256, 128, 64}) {
+    for (int rot : {4, 1}) {
+      for (int b_lbo : {n * 16, 8192}) {
+        for (int a_lbo : {8192, 16384 - 8192 + 2880, 2880, 5184, 2048}) {
+          for (int a_sbo : {256, 128, 160, 288}) {
+            if (a_lbo == 2048 && a_sbo != 128) continue;                 // dense 128-row tile: k-slices back to back
+            if ((a_lbo == 2880 && a_sbo != 160) || (a_lbo == 5184 && a_sbo != 288)) continue;   // the halo tiles of modconv_halo
+            for (int a_off : {0, 176}) {
+              if (a_off && a_sbo != 160) continue;
+              Pattern p = {1, {n}, {0}, {0}, {0}, {0}, 8000, a_lbo, a_sbo, b_lbo, rot, a_off};
+              const double c = time_pattern(p, sms, cyc, ns, smem);
+              printf("%-5d %-7d %-6d %-6d %-6d %-4d | %10.2f\n", n, a_lbo, a_sbo, a_off, b_lbo, rot, c);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Is the N=256 stream POWER-bound with realistic operands?  Same MMA stream, constant vs random data, short vs long runs.
+static void run_power(int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
+  printf("\n%-6s %-6s %-9s | %10s %10s %10s\n", "N", "data", "MMAs", "ns/MMA", "cyc/MMA", "TF/s chip");
+  for (int n : {256, 128}) {
+    for (int rnd : {0, 1}) {
+      for (int it : {8000, 400000}) {
+        Pattern p = {1, {n}, {0}, {0}, {0}, {0}, it, 0, 0, 0, 4, 0, rnd};
+        launch_pattern<1>(p, sms, cyc, ns, smem);
+        if (cudaDeviceSynchronize() != cudaSuccess) return;
+        std::vector<unsigned long long> hc(sms), hn(sms);
+        cudaMemcpy(hc.data(), cyc, sms * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hn.data(), ns, sms * 8, cudaMemcpyDeviceToHost);
+        double mc = 0, mn = 0;
+        for (int i = 0; i < sms; ++i) {
+          mc += hc[i];
+          mn += hn[i];
+        }
+        mc /= sms * (double)it;
+        mn /= sms * (double)it;
+        printf("%-6d %-6s %-9d | %10.2f %10.2f %10.1f\n", n, rnd ? "random" : "const", it, mn, mc, 2.0 * 128 * 16 * n / mn * sms / 1e3);
+      }
+    }
+  }
 }
 
 static void run_patterns(int sms, unsigned long long* cyc, unsigned long long* ns, int smem) {
@@ -252,6 +326,14 @@ int main(int argc, char** argv) {
   cudaMalloc(&sink, 4);
   if (argc > 1 && argv[1][0] == 'p') {
     run_patterns(sms, cyc, ns, smem);
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'w') {
+    run_power(sms, cyc, ns, smem);
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'l') {
+    run_layout_sweep(sms, cyc, ns, smem);
     return 0;
   }
   std::vector<Case> cases;
