@@ -581,8 +581,18 @@ bool halo_eligible(const sgr_conv_args* a) {
 // memory bandwidth: MMA operand reads + producer loads run at ~125 of 128 B/clk), net 3.22 vs 3.40 ms.  With the FIR work
 // switched off (SGR_DEBUG=512, handshakes only) the step is 2.96 ms, the bound a cheaper producer can approach.
 bool halo_fusable(const sgr_conv_args* a) {
-  static const bool on = [] { const char* e = getenv("SGR_FUSE_FIR"); return !(e && e[0] == '0'); }();
-  if (!(on && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0)) return false;
+  // SGR_FUSE_FIR: 0 = never, 1 = wherever possible, unset = consumers with at least 128 input channels.  Measured on one B200
+  // (B = 32, 256^2 / cm1, tools/gpu/call18.sh), fused producers vs the separate FIR pass (up_finish_kernel) per consumer:
+  //   512 ch @ 16^2 + 32^2: consumer +0.030 ms, pass 0.072 ms   256 ch @ 64^2: +0.029 vs 0.072   128 ch @ 128^2: +0.098 vs 0.132
+  //   64 ch @ 256^2: +0.247 vs 0.239 — a wash: that consumer is bound by shared-memory bandwidth (operand reads + producers
+  //   ~0.85 wavefronts per cycle), so it runs the plain kernel (0.45 ms, at the N = 64 MMA rate) behind the HBM-bound pass.
+  // Whole step: all fused 3.10 .. 3.15 ms, none 3.18 ms, this policy the same as all fused.
+  static const int min_cin = [] {
+    const char* e = getenv("SGR_FUSE_FIR");
+    if (!e) return 128;
+    return (e[0] == '0' && !e[1]) ? (1 << 30) : 0;
+  }();
+  if (!(a->cin >= min_cin && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0)) return false;
   // layers with fewer tiles than half the SMs (small batches) run split-K, which the fused producers do not support
   const int nt = a->column_tile > 0 ? a->column_tile : pick_nt(a->cout);
   const int mt = nt <= 128 ? 2 : 1;

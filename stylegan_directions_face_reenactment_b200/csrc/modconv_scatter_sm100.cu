@@ -44,13 +44,15 @@ __device__ __forceinline__ int scatter_prefix(int nt, int sft) {                
   return sft == 0 ? 0 : (sft == 1 ? nt : (sft == 2 ? nt + nt / 2 : 2 * nt));
 }
 
-template <int NT, int HE>      // HE: box entries per chunk-plane of the wrapped-halo tiles (144 or 140), 0 = dense-box tiles
+template <int NT, int HE>      // HE > 0: box entries per chunk-plane of the wrapped-halo tiles (144 or 140); HE < 0: dense-box tiles of
+                               // exactly -HE rows (121 = the 11 x 11 box of the 33^2 / 65^2 grids); 0: dense-box tiles of any shape
 __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap tmap_out,
                                                                 const ConvKernelParams p) {
   using Cfg = ScatterCfg<NT>;
-  constexpr bool HALO = HE != 0;
-  constexpr int kHE = HE != 0 ? HE : 144;
+  constexpr bool HALO = HE > 0;
+  constexpr int kHE = HE > 0 ? HE : (HE < 0 ? -HE : 144);      // entries per chunk-plane when they are a compile-time constant
+  constexpr bool kFixed = HE != 0;
   constexpr int AS = Cfg::kAStages, BSL = Cfg::kBSlabs;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // every MMA's operands are base + compile-time constant (wrapped-halo tiles have a FIXED chunk stride of kHaloEntries
     // box entries for that; the dense-box tiles keep run-time strides).
     if (lane == 0) {
-      const uint32_t a_lbo = HALO ? kHE * 16u : static_cast<uint32_t>(p.rows) * 16u;   // bytes per chunk-plane of a box
+      const uint32_t a_lbo = kFixed ? kHE * 16u : static_cast<uint32_t>(p.rows) * 16u;   // bytes per chunk-plane of a box
       const uint64_t a_ring = umma_desc(smem_u32(a_base), a_lbo, 128);
       // wrapped-halo tiles: M row r of shift (a, b) = box entry bw + 1 + r - (a * bw + b)
       const uint64_t h_off[4] = {static_cast<uint64_t>(p.bw + 1), static_cast<uint64_t>(p.bw), 1, 0};
@@ -172,16 +174,18 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const uint64_t grp_off = static_cast<uint64_t>(grp) * (Cfg::kGroupBytes >> 4);
           const bool b_skip = (p.debug & 4) && g >= Cfg::kGroups;
           const uint32_t acc0 = kc != 0 ? 1u : 0u;
-          if (HALO && !p.single) {
-            if (!((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
+          if (kFixed && !p.single) {
+            if (HALO && !((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
             const uint64_t a_st = a_ring + static_cast<uint64_t>(hs) * (Cfg::kHaloStageBytes >> 4);
 #pragma unroll
             for (int sft = 0; sft < 4; ++sft) {
               constexpr uint32_t kCol[4] = {0, 0, NT / 4, NT / 4};          // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
               const uint32_t n_s = scatter_rows(NT, sft);
+              if (!HALO) mbar_wait(&a_full[sft], a_par);
               if (!b_skip) mbar_wait(&b_full[grp * 4 + sft], gphase);
               tc_fence_after();
-              const uint64_t a_s = a_st + h_off[sft], b_s = b_ring[sft] + grp_off;
+              const uint64_t a_s = HALO ? a_st + h_off[sft] : a_ring + static_cast<uint64_t>((sft * kABytes) >> 4);
+              const uint64_t b_s = b_ring[sft] + grp_off;
 #pragma unroll
               for (int j = 0; j < kBlockK / 16; ++j) {
                 const uint64_t bj = static_cast<uint64_t>(j) * ((n_s * 32) >> 4), blo = (n_s * 64) >> 4;
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
                 umma_bf16(d_tmem + kCol[sft], a_s + j * kHJ, b_s + (bj + blo), idesc[sft], 1);
                 umma_bf16(d_tmem + kCol[sft], a_s + j * kHJ, b_s + bj, idesc[sft], 1);
               }
-              if (sft == 3) umma_commit(&a_empty[hs]);
+              if (!HALO) umma_commit(&a_empty[sft]);
+              else if (sft == 3) umma_commit(&a_empty[hs]);
               umma_commit(&b_empty[grp * 4 + sft]);
             }
           } else {
@@ -347,6 +352,8 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
       e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 140>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, -121>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("upconv_scatter: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return 1;
@@ -365,6 +372,8 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
     upconv_scatter_kernel<NT, 144><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
   else if (he == 140)
     upconv_scatter_kernel<NT, 140><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+  else if (he == 0 && p.rows == 121)
+    upconv_scatter_kernel<NT, -121><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
   else if (he == 0)
     upconv_scatter_kernel<NT, 0><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
   else {

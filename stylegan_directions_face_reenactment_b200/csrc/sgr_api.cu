@@ -33,8 +33,10 @@ static cudaEvent_t g_prof_ev[kProfCap][2];
 static int g_prof_tag[kProfCap];
 static int g_prof_made = 0, g_prof_n = 0;
 
+static int g_prof_layer = 0;          // styled-layer index of the launches being timed (sgr_synthesis_forward sets it)
 static bool prof_begin(cudaStream_t st, int tag = 0) {
   if (!g_prof_on || g_prof_n >= kProfCap) return false;
+  tag += 16 * g_prof_layer;           // tag & 15: 0 GEMM, 1 FIR pass; tag >> 4: layer
   while (g_prof_made <= g_prof_n) {
     cudaEventCreate(&g_prof_ev[g_prof_made][0]);
     cudaEventCreate(&g_prof_ev[g_prof_made][1]);
@@ -466,7 +468,10 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
       nx.column_tile = net->styled[l + 1].column_tile;
       defer = halo_fusable(&nx);
     }
-    if (modconv_forward_impl(&a, have_pending ? &pending_up : nullptr, defer, stream)) return 1;
+    g_prof_layer = l;
+    const int rc_layer = modconv_forward_impl(&a, have_pending ? &pending_up : nullptr, defer, stream);
+    g_prof_layer = 0;
+    if (rc_layer) return 1;
     have_pending = defer;
     if (defer) pending_up = a;
     if (L.up) res *= 2;
