@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
     }
   } else if (FUSED && warp == 3) {
     // ------------------------------------------------------------------ parity-plane TMA issuer (fused mode)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t ai = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile / p.m_tiles;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t ai = 0, bi = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ks = tile % p.ksplit, otile = tile / p.ksplit;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
     // shared-memory descriptors per MMA (~20 instructions: 170-180 cycles per N = 256 MMA, 100 per N = 128 MMA measured with
     // all loads switched off).  Here: ring base descriptors once, one per stage / slab by a multiply-add, the nine taps fully
     // unrolled so that every MMA's operands are base + compile-time constant.
-    if (lane == 0 && !kPacedIssue) {
+    if (!kPacedIssue && elect_one_sync()) {
       const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
       const uint32_t idesc_cat = umma_idesc(p.fmt, kTileM, Cfg::kConcat ? 2 * NT : NT);
       constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;
@@ -590,7 +590,9 @@ bool halo_fusable(const sgr_conv_args* a) {
   static const int min_cin = [] {
     const char* e = getenv("SGR_FUSE_FIR");
     if (!e) return 128;
-    return (e[0] == '0' && !e[1]) ? (1 << 30) : 0;
+    if (e[0] == '0' && !e[1]) return 1 << 30;
+    if (e[0] == '1' && !e[1]) return 0;
+    return atoi(e);                                   // any other number: the minimum input-channel count of a fused consumer
   }();
   if (!(a->cin >= min_cin && halo_eligible(a) && !a->single_pass && a->cin % 32 == 0 && a->h_in % 2 == 0 && a->w_in % 2 == 0)) return false;
   // layers with fewer tiles than half the SMs (small batches) run split-K, which the fused producers do not support

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t a_bytes = static_cast<uint32_t>(p.rows) * (p.single ? 64u : 128u);   // single pass: hi plane only
       const uint32_t halo_bytes = static_cast<uint32_t>(kHE) * (p.single ? 64u : 128u);      // box = bw x box_rows entries
       const uint32_t b_row = p.single ? 64u : 128u;                                       // slabs are plane-major: hi half first
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     // per MMA.  Ring base descriptors are built once; per channel block one multiply-add per ring, per shift one add, and
     // every MMA's operands are base + compile-time constant (wrapped-halo tiles have a FIXED chunk stride of kHaloEntries
     // box entries for that; the dense-box tiles keep run-time strides).
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t a_lbo = kFixed ? kHE * 16u : static_cast<uint32_t>(p.rows) * 16u;   // bytes per chunk-plane of a box
       const uint64_t a_ring = umma_desc(smem_u32(a_base), a_lbo, 128);
       // wrapped-halo tiles: M row r of shift (a, b) = box entry bw + 1 + r - (a * bw + b)

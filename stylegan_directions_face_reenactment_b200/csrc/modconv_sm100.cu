@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ks = tile % p.ksplit;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // A stage image: [plane][chunk][row][8] with `rows` dense rows per chunk (the TMA box), rows <= 128
       // (issuing thread = critical resource, see modconv_halo_sm100.cu: stage base descriptors by one multiply-add, the six
       //  MMAs of a stage at base + loop-invariant offsets)

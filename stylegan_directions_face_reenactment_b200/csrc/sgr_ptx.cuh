@@ -14,6 +14,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  Code guarded by `if (elect_one_sync())` is known to ptxas to
+// run in a single thread: tcgen05.mma / TMA instructions in it are emitted back to back, whereas the same code under
+// `if (lane == 0)` gets a 5-instruction ELECT / PLOP3 / BRA.U.ANY wrapper around EVERY such instruction — and the issuing
+// thread (~8 cycles per instruction) is the critical resource of the GEMM kernels.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

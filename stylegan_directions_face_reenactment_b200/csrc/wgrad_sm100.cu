@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const WgItem w = wg_decode(p, item);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = wg_idesc(p.nt);
       const uint32_t a_plane = 16 * p.a_sbo;                       // 16 chunks per plane of the gz box
       const uint32_t b_sbo = kWgPix * 16, b_plane = (p.nt / 8) * b_sbo;
