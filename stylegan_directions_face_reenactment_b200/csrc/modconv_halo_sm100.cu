@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
                                                                             const ConvKernelParams p, const FusedFirParams f) {
   using Cfg = HaloCfg<NT, MT, FUSED>;
   constexpr int AS = Cfg::kAStages, BS = Cfg::kBStages;
-  constexpr bool kPacedIssue = FUSED && NT <= 128;      // see the two MMA issuers below
+#ifndef SGR_PACED_MODE
+#define SGR_PACED_MODE 0
+#endif
+  constexpr bool kPacedIssue = SGR_PACED_MODE == 1 ? false : (FUSED && NT <= 128);      // see the two MMA issuers below
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* a_empty = a_full + AS;
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
     // bound by shared-memory bandwidth (MMA operand reads + FIR producers ~0.85 wavefronts / cycle); measured on the same B200,
     // the streamlined issuer above makes them SLOWER (64 -> 64 @ 256^2: 0.69 -> 0.80 ms, 128 -> 128 @ 128^2: 0.49 -> 0.50 ms):
     // bursts of operand reads starve the producer warps.  Everywhere else it wins (512 -> 512 @ 32^2: 0.40 -> 0.36 ms).
-    if (lane == 0 && kPacedIssue) {
+    if (kPacedIssue && (SGR_PACED_MODE == 2 ? elect_one_sync() : lane == 0)) {
       const uint32_t idesc = umma_idesc(p.fmt, kTileM, NT);
       const uint32_t idesc_cat = umma_idesc(p.fmt, kTileM, Cfg::kConcat ? 2 * NT : NT);
       constexpr uint32_t kALbo = Cfg::kChunkBytes, kASbo = Cfg::kHW * 16, kAPlane = Cfg::kChunkBytes * 4;

@@ -7,10 +7,12 @@ keys and shapes (model.py:361-539; key list in SURVEY.md §8b) — so reference 
 run_inference.py / run_trainer.py can import this class through the namespace overlay in overlay/libs.
 
 The arithmetic is NOT the reference's: the per-sample modulation is moved from the weights to the activations
-(y = d[b,o] * conv(x * s[b,i], W)), the transposed conv + blur of the upsampling layers is one
-polyphase convolution (§9.2), and conv + noise + bias + leaky-relu (+ the next ToRGB) run as one tcgen05 kernel per layer
-(csrc/modconv_sm100.cu).  The fp32 nn.Parameters stay the source of truth; packed bf16 hi/lo weights are a cache keyed on
-each parameter's version counter.
+(y = d[b,o] * conv(x * s[b,i], W)); the transposed conv of an upsampling layer runs in scatter form (its 9
+real taps as one tcgen05 GEMM onto four parity planes, csrc/modconv_scatter_sm100.cu) and the separable 4x4 blur + noise + bias
++ leaky-relu are applied on the way into the next convolution (fused producer warps or the HBM-bound up_finish_kernel; the
+polyphase folding W (*) fir of SURVEY §9.2 survives only for non-separable blur kernels); a plain conv + noise + bias +
+leaky-relu (+ the next ToRGB) is one tcgen05 kernel per layer (csrc/modconv_halo_sm100.cu).  The fp32 nn.Parameters stay the
+source of truth; packed bf16 hi/lo weights are a cache keyed on each parameter's version counter.
 """
 import ctypes as C
 import math
@@ -409,6 +411,16 @@ class Generator(nn.Module):
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
         image = self.synthesis(latent, noise)
         return (image, latent) if return_latents else (image, None)
+
+    def invalidate_cache(self):
+        """Drop every derived object (packed tensor-core weights, cached C descriptors, captured CUDA graphs, workspaces).  The
+        caches are keyed on each parameter's (data_ptr, _version), which optimizers, `copy_`, `load_state_dict` and `.to()` all
+        change; a write through `param.data` does not — call this after one."""
+        for layer in self.styled_layers() + self.rgb_layers():
+            layer.conv._pack_cache.clear()
+        self.__dict__.pop('_desc_cache', None)
+        self._workspace.clear()
+        return self
 
     def enable_cuda_graphs(self, on=True):
         """Replay the synthesis kernels of no-grad forward calls as one captured CUDA graph per (batch, weights, noise)
