@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : 256, 1) modconv_halo_k
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();      // the next kernel may set itself up on SMs this grid has left
+  pdl_wait();                   // nothing above reads what the previous kernel wrote
 
   const int out_tiles = p.m_tiles * p.n_tiles;
   const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice of channel blocks)
@@ -556,8 +558,13 @@ static int launch_halo_impl(const ConvKernelParams& p, const CUtensorMap& tmap, 
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   CUtensorMap tmap_planes = tmap;            // not fused: unused placeholder
   if (FUSED && make_plane_tensor_map(&tmap_planes, f.t, p.B, f.C, f.Hin + 1, f.Win + 1, Cfg::kPC)) return 1;
-  modconv_halo_kernel<NT, MT, FUSED><<<std::min(total, sms), FUSED ? kFusedThreads : 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_planes, p, f);
+  const cudaError_t le = launch_pdl(modconv_halo_kernel<NT, MT, FUSED>, dim3(std::min(total, sms)), dim3(FUSED ? kFusedThreads : 256),
+                                    Cfg::kSmemBytes, stream, tmap, tmap_planes, p, f);
   count_launch();
+  if (le != cudaSuccess) {
+    set_error("modconv_halo_kernel: launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return check_launch("modconv_halo_kernel") ? 0 : 1;
 }
 

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = 4 * p.kchunks;                  // k = kc * 4 + shift
@@ -368,19 +370,24 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
   q.tma_store = (!tma_off && p.bb == 1 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;
   if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
   const int he = p.halo ? p.bw * p.box_rows : 0;
+  cudaError_t le = cudaSuccess;
   if (he == 144)
-    upconv_scatter_kernel<NT, 144><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+    le = launch_pdl(upconv_scatter_kernel<NT, 144>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
   else if (he == 140)
-    upconv_scatter_kernel<NT, 140><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+    le = launch_pdl(upconv_scatter_kernel<NT, 140>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
   else if (he == 0 && p.rows == 121)
-    upconv_scatter_kernel<NT, -121><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+    le = launch_pdl(upconv_scatter_kernel<NT, -121>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
   else if (he == 0)
-    upconv_scatter_kernel<NT, 0><<<std::min(total, sms), 256, Cfg::kSmemBytes, stream>>>(tmap, tmap_out, q);
+    le = launch_pdl(upconv_scatter_kernel<NT, 0>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
   else {
     set_error("upconv_scatter: unsupported halo box of %d entries", he);
     return 1;
   }
   count_launch();
+  if (le != cudaSuccess) {
+    set_error("upconv_scatter_kernel: launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return check_launch("upconv_scatter_kernel") ? 0 : 1;
 }
 

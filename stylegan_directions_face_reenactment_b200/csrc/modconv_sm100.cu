@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(256, 1) modconv_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int out_tiles = p.m_tiles * p.n_tiles;
   const int total_tiles = out_tiles * p.ksplit;          // work item = (output tile, K slice); slice fastest
@@ -252,8 +254,12 @@ static int launch_nt(const ConvKernelParams& p, const CUtensorMap& tmap, cudaStr
   }
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(total, sms);
-  modconv_kernel<NT><<<grid, 256, ConvCfg<NT>::kSmemBytes, stream>>>(tmap, p);
+  const cudaError_t le = launch_pdl(modconv_kernel<NT>, dim3(grid), dim3(256), ConvCfg<NT>::kSmemBytes, stream, tmap, p);
   count_launch();
+  if (le != cudaSuccess) {
+    set_error("modconv_kernel: launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return check_launch("modconv_kernel") ? 0 : 1;
 }
 

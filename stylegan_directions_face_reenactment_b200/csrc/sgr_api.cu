@@ -1,5 +1,6 @@
 // extern "C" surface of libsgr.so (include/sgr.h) and the whole-network orchestration.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -17,6 +18,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { ++g_launches; }
+// Programmatic dependent launch of the forward chain (sgr_internal.h launch_pdl, sgr_ptx.cuh pdl_wait): OFF by default.
+// Measured on one B200 (B = 32, 256^2, tools/gpu/call25.sh, same box): 3.04 ms per step without, 3.17 ms with it (sustained
+// 3.27 vs 3.43 ms) — the persistent GEMM CTAs hold a whole SM's shared memory and TMEM, so a dependent CTA can only become
+// resident when a primary CTA has already exited, and the early-resident CTAs then sit in griddepcontrol.wait holding that
+// SM; nothing of the ~3 us prologue is recovered.  SGR_PDL=1 enables it (results are identical either way).
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SGR_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
 bool check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

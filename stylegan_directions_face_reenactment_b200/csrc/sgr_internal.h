@@ -30,6 +30,24 @@ void tile_box(int h, int w, int* bw, int* bh, int* bb);
 void tile_box_search(int batch, int h, int w, int* bw, int* bh, int* bb);
 
 void set_error(const char* fmt, ...);
+bool pdl_enabled();          // SGR_PDL=0 disables programmatic dependent launch (sgr_api.cu)
+
+// Launch with programmatic stream serialization: the kernel may start while its predecessor drains (sgr_ptx.cuh pdl_wait()).
+// ONLY for kernels that call pdl_wait() before their first dependent global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 void count_launch();
 bool check_launch(const char* what);
 

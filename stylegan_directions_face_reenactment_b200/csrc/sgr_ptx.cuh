@@ -28,6 +28,14 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in the
+// stream is still running (as SMs free up); it must not touch anything the predecessor produces before pdl_wait() returns
+// (= all prerequisite grids complete, their writes visible).  pdl_launch_dependents() lets the NEXT kernel do the same.
+// Everything before pdl_wait() — barrier init, TMEM allocation, descriptor prefetch — overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

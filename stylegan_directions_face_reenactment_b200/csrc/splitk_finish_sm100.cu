@@ -14,6 +14,8 @@ namespace sgr {
 constexpr int kColGroups = 4;
 __global__ void __launch_bounds__(128 * kColGroups) splitk_finish_kernel(const ConvKernelParams p) {
   __shared__ float rgb_red[kColGroups][128][3];
+  pdl_launch_dependents();
+  pdl_wait();                                        // the partial sums come from the GEMM launch right before
   const int r = threadIdx.x & 127;
   const int cg = threadIdx.x >> 7;
   const int sub_tiles = p.halo_mt > 0 ? p.halo_mt : 1;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(128 * kColGroups) splitk_finish_kernel(const C
 int splitk_finish_launch(const ConvKernelParams& p, cudaStream_t stream) {
   const int sub_tiles = p.halo_mt > 0 ? p.halo_mt : 1;
   dim3 grid(p.m_tiles * sub_tiles, p.n_tiles);
-  splitk_finish_kernel<<<grid, 128 * kColGroups, 0, stream>>>(p);
+  launch_pdl(splitk_finish_kernel, grid, dim3(128 * kColGroups), 0, stream, p);
   count_launch();
   return check_launch("splitk_finish_kernel") ? 0 : 1;
 }

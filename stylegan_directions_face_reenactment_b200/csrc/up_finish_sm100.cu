@@ -86,6 +86,8 @@ template <int ROWS, int FMT, bool F32OUT>
 __global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams p) {
   // sc[0..3] = gy (vertical taps, flipped), sc[4..7] = gx (horizontal taps, flipped, normalised by the tap sum)
   __shared__ float sc[8];
+  pdl_launch_dependents();
+  pdl_wait();                                        // the parity planes come from the scatter GEMM right before
   if (threadIdx.x < 4) {
     const int a = threadIdx.x;
     float rs = 0.f, cs = 0.f, tot = 0.f;
@@ -263,11 +265,11 @@ template <int ROWS>
 static void up_finish_dispatch(const UpFinishParams& p, dim3 grid, int threads, cudaStream_t st) {
   const bool f32 = p.out_f32 != nullptr;
   if (p.out_fmt == kFmtBF16) {
-    if (f32) up_finish_kernel<ROWS, kFmtBF16, true><<<grid, threads, 0, st>>>(p);
-    else up_finish_kernel<ROWS, kFmtBF16, false><<<grid, threads, 0, st>>>(p);
+    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtBF16, true>, grid, dim3(threads), 0, st, p);
+    else launch_pdl(up_finish_kernel<ROWS, kFmtBF16, false>, grid, dim3(threads), 0, st, p);
   } else {
-    if (f32) up_finish_kernel<ROWS, kFmtFP16, true><<<grid, threads, 0, st>>>(p);
-    else up_finish_kernel<ROWS, kFmtFP16, false><<<grid, threads, 0, st>>>(p);
+    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtFP16, true>, grid, dim3(threads), 0, st, p);
+    else launch_pdl(up_finish_kernel<ROWS, kFmtFP16, false>, grid, dim3(threads), 0, st, p);
   }
 }
 

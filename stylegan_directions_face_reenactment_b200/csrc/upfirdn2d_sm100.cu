@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "sgr_internal.h"
+#include "sgr_ptx.cuh"
 
 namespace sgr {
 
@@ -379,6 +380,8 @@ __global__ void torgb_tail_kernel(const float* __restrict__ rgb_acc, int slots, 
                                   const float* __restrict__ skip_in, const float* __restrict__ fir,
                                   float* __restrict__ out, int planes, int H, int W) {
   __shared__ float sk[16];
+  pdl_launch_dependents();
+  pdl_wait();                                        // the ToRGB partial sums come from the convolution right before
   if (threadIdx.x < 16) sk[threadIdx.x] = fir ? fir[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)] : 0.f;
   __syncthreads();
   // grid: (x groups of 4 pixels, y, plane) - no integer divisions in the kernel
@@ -427,7 +430,7 @@ int torgb_tail_launch(const float* rgb_acc, int slots, const float* bias, const 
   const int threads = W / 4 >= 128 ? 128 : (W / 4 >= 64 ? 64 : 32);
   const int planes = batch * 3;
   dim3 grid((W / 4 + threads - 1) / threads, H, planes < 65535 ? planes : 65535);
-  torgb_tail_kernel<<<grid, threads, 0, st>>>(rgb_acc, slots, bias, skip_in, fir, out, planes, H, W);
+  launch_pdl(torgb_tail_kernel, grid, dim3(threads), 0, st, rgb_acc, slots, bias, skip_in, fir, out, planes, H, W);
   count_launch();
   return check_launch("torgb_tail_kernel") ? 0 : 1;
 }
@@ -441,6 +444,8 @@ __global__ void torgb_tail_u8_kernel(const float* __restrict__ rgb_acc, int slot
                                      const float* __restrict__ skip_in, const float* __restrict__ fir,
                                      unsigned char* __restrict__ out, int batch, int H, int W, int out_h, int out_w) {
   __shared__ float sk[16];
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x < 16) sk[threadIdx.x] = fir ? fir[(3 - threadIdx.x / 4) * 4 + (3 - threadIdx.x % 4)] : 0.f;
   __syncthreads();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
@@ -498,7 +503,7 @@ int torgb_tail_u8_launch(const float* rgb_acc, int slots, const float* bias, con
   }
   const int threads = out_w >= 128 ? 128 : (out_w >= 64 ? 64 : 32);
   dim3 grid((out_w + threads - 1) / threads, out_h, batch);
-  torgb_tail_u8_kernel<<<grid, threads, 0, st>>>(rgb_acc, slots, bias, skip_in, fir, out, batch, H, W, out_h, out_w);
+  launch_pdl(torgb_tail_u8_kernel, grid, dim3(threads), 0, st, rgb_acc, slots, bias, skip_in, fir, out, batch, H, W, out_h, out_w);
   count_launch();
   return check_launch("torgb_tail_u8_kernel") ? 0 : 1;
 }
