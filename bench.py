@@ -105,12 +105,15 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """DRAM bytes (read + write) of the conv GEMM launches of one step from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json, written by tools/ncu_summary.py); None if no capture has been summarised."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-            return json.load(f)['conv_dram_bytes_per_step']
-    except Exception:
-        return None
+    (profiles/r2_traffic.json, written by tools/ncu_summary.py; r1_traffic.json as fallback); None if no capture has been
+    summarised."""
+    for name in ('r2_traffic.json', 'r1_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                return json.load(f)['conv_dram_bytes_per_step']
+        except Exception:
+            continue
+    return None
 
 
 def conv_flops_per_frame():

@@ -161,6 +161,7 @@ __global__ void wsq_kernel(const float* __restrict__ w, int cout, int cin, int n
 // One warp per (job, i, group of 4 samples): s[b,i] = <latent[b,row,:], W[i,:]> / sqrt(512) + bias[i]
 // (model.py:148-157 with lr_mul = 1).  The weight row stays in registers; the four samples are independent chains.
 constexpr int kStyleBatchGroup = 4;
+constexpr int kStyleGroupsPerWarp = 4;
 __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ latent, int latent_stride, int batch) {
   const StyleJob& j = jobs.job[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +173,11 @@ __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ lat
   for (int q = 0; q < 4; ++q) wv[q] = __ldg(wrow + q * 32 + lane);
   const float bias = __ldg(j.mod_bias + i);
   const float scale = 0.044194173824159216f;   // 1/sqrt(512)
-  const int b0 = blockIdx.z * kStyleBatchGroup;
+  // the weight row in registers serves kStyleGroupsPerWarp groups of samples (one group per warp re-read the 12 MB of
+  // modulation weights once per four samples: 35 us per step at B = 32)
+  for (int g = 0; g < kStyleGroupsPerWarp; ++g) {
+  const int b0 = (blockIdx.z * kStyleGroupsPerWarp + g) * kStyleBatchGroup;
+  if (b0 >= batch) break;
   float acc[kStyleBatchGroup];
 #pragma unroll
   for (int u = 0; u < kStyleBatchGroup; ++u) {
@@ -195,6 +200,7 @@ __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ lat
 #pragma unroll
     for (int u = 1; u < kStyleBatchGroup; ++u) v = lane == u ? acc[u] : v;
     j.out[static_cast<size_t>(b0 + lane) * j.cin + i] = fmaf(v, scale, bias);
+  }
   }
 }
 
@@ -399,7 +405,7 @@ int pack_weight_launch(const float* w, const float* fir, int cout, int cin, int 
 int style_jobs_launch(const StyleJobs& jobs, const float* latent, int latent_stride, int batch, cudaStream_t st) {
   int cmax = 0;
   for (int i = 0; i < jobs.n; ++i) cmax = cmax > jobs.job[i].cin ? cmax : jobs.job[i].cin;
-  dim3 grid((cmax + 7) / 8, jobs.n, (batch + kStyleBatchGroup - 1) / kStyleBatchGroup);
+  dim3 grid((cmax + 7) / 8, jobs.n, (batch + kStyleBatchGroup * kStyleGroupsPerWarp - 1) / (kStyleBatchGroup * kStyleGroupsPerWarp));
   style_kernel<<<grid, 256, 0, st>>>(jobs, latent, latent_stride, batch);
   count_launch();
   return check_launch("style_kernel") ? 0 : 1;

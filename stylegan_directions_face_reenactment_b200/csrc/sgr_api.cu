@@ -61,6 +61,33 @@ static void prof_end(cudaStream_t st) {
   ++g_prof_n;
 }
 
+// Side stream for the ToRGB tails: rgb_r = slot sum + bias + 2x FIR(skip_{r-1}) only feeds the next tail and, at the end, the
+// image — never a convolution — so the seven small, latency-bound launches (6..9 us each, 2 % of a B = 32 step) leave the
+// critical path: forked after the convolution that produced the partial sums, joined once before the call returns (the
+// pattern is capturable into a CUDA graph).  One stream + event set per device, created on first use.  SGR_TAIL_STREAM=0: off.
+struct TailStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[SGR_MAX_RGB] = {};
+  cudaEvent_t join = nullptr;
+  bool ok = false;
+};
+static TailStream* tail_stream() {
+  static const bool off = [] { const char* e = getenv("SGR_TAIL_STREAM"); return e && e[0] == '0'; }();
+  if (off) return nullptr;
+  static TailStream per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  TailStream& t = per_dev[dev];
+  if (!t.ok) {
+    if (cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < SGR_MAX_RGB; ++i)
+      if (cudaEventCreateWithFlags(&t.fork[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    t.ok = true;
+  }
+  return &t;
+}
+
 static bool have_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -422,6 +449,8 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
     return 1;
 
   // 4. the layer chain
+  TailStream* tails = g_prof_on ? nullptr : tail_stream();      // per-launch event timing keeps everything on one stream
+  bool forked = false;
   int res = 4;
   int skip_cur = 0;
   const float* prev_skip = nullptr;
@@ -493,16 +522,27 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
         set_error("synthesis_forward: rgb %d needs an upsample kernel", r);
         return 1;
       }
+      cudaStream_t ts = st;
+      if (tails && cudaEventRecord(tails->fork[r], st) == cudaSuccess &&
+          cudaStreamWaitEvent(tails->side, tails->fork[r], 0) == cudaSuccess) {
+        ts = tails->side;
+        forked = true;
+      }
       if (last && frames_u8 &&
           torgb_tail_u8_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, frames_u8, batch, res, res,
-                               extras->u8_h, extras->u8_w, st))
+                               extras->u8_h, extras->u8_w, ts))
         return 1;
       if ((!last || image) &&
-          torgb_tail_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, dst, batch, res, res, st))
+          torgb_tail_launch(F(pl.rgbacc_off[r]), pl.rgb_slots[r], R.bias, prev_skip, R.fir, dst, batch, res, res, ts))
         return 1;
       prev_skip = dst;
       skip_cur = 1 - skip_cur;
     }
+  }
+  if (forked && (cudaEventRecord(tails->join, tails->side) != cudaSuccess ||
+                 cudaStreamWaitEvent(st, tails->join, 0) != cudaSuccess)) {
+    set_error("synthesis_forward: joining the ToRGB side stream failed");
+    return 1;
   }
   if (res != net->size) {
     set_error("synthesis_forward: layer chain ends at %d, expected %d", res, net->size);
