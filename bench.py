@@ -587,19 +587,24 @@ def main():
     copy_stream = torch.cuda.Stream(device=device)
     done = [torch.cuda.Event(), torch.cuda.Event()]
 
+    live = [None, None]                                        # frames whose device->host copy may still be in flight
+
     def step_e2e(i):
+        slot = i % 2
+        # the frame copied two steps ago must have left the device before its memory is handed back to the allocator (a GPU-side
+        # wait; record_stream() would defer the release to an allocator-internal event and occasionally forces a cudaMalloc)
+        torch.cuda.current_stream().wait_event(done[slot])
         with torch.no_grad():
             dp = dp_host[i % len(dp_host)].to(device, non_blocking=True)
             img = pkg.generate_image(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
                                      input_is_latent=True)
         ready = torch.cuda.Event()
         ready.record()
-        slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ready)
             out_host[slot].copy_(img, non_blocking=True)
-            img.record_stream(copy_stream)
             done[slot].record(copy_stream)
+        live[slot] = img
 
     def finish_e2e():                                          # the last copies end inside the timed region
         for ev in done:
@@ -614,18 +619,19 @@ def main():
     u8_host = [torch.empty(BATCH, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     def step_e2e_u8(i):
+        slot = i % 2
+        torch.cuda.current_stream().wait_event(done[slot])
         with torch.no_grad():
             dp = dp_host[i % len(dp_host)].to(device, non_blocking=True)
             u8 = pkg.generate_frames_uint8(G, wsrc, 0.7, trunc, w_plus=True, num_layers_shift=8, shift_code=A(dp),
                                            input_is_latent=True)
         ready = torch.cuda.Event()
         ready.record()
-        slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ready)
             u8_host[slot].copy_(u8, non_blocking=True)
-            u8.record_stream(copy_stream)
             done[slot].record(copy_stream)
+        live[slot] = u8
 
     for i in range(3):
         step_e2e_u8(i)

@@ -69,6 +69,7 @@ struct TailStream {
   cudaStream_t side = nullptr;
   cudaEvent_t fork[SGR_MAX_RGB] = {};
   cudaEvent_t join = nullptr;
+  cudaEvent_t prep_fork = nullptr, prep_join = nullptr;      // styles / tables of the later layers (see sgr_synthesis_forward)
   bool ok = false;
 };
 static TailStream* tail_stream() {
@@ -83,6 +84,9 @@ static TailStream* tail_stream() {
     for (int i = 0; i < SGR_MAX_RGB; ++i)
       if (cudaEventCreateWithFlags(&t.fork[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.prep_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t.prep_join, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
     t.ok = true;
   }
   return &t;
@@ -399,25 +403,32 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   const int latent_stride = net->n_latent * SGR_STYLE_DIM;
 
-  // 1. every layer's style vector in one launch
-  StyleJobs sj;
-  sj.n = 0;
+  // 1 + 2. style vectors, demodulation and epilogue tables (next layer's style, fused ToRGB coefficients).  The first kSplit
+  // layers (4^2, 8^2: latency-bound GEMMs that leave the SMs mostly idle) only need their own share; the rest of the
+  // modulation GEMVs / table GEMMs (~80 % of the work, ~35 us at B = 32) runs on the side stream underneath them and is joined
+  // before layer kSplit.
+  TailStream* tails = g_prof_on ? nullptr : tail_stream();      // per-launch event timing keeps everything on one stream
+  constexpr int kSplit = 4;
+  const bool split_prep = tails != nullptr && net->n_styled > kSplit + 1;
+  const int n_first = split_prep ? kSplit : net->n_styled;      // tables of layers [0, n_first) come first
+  StyleJobs sj[2];
+  sj[0].n = sj[1].n = 0;
   for (int l = 0; l < net->n_styled; ++l) {
     const sgr_styled_layer& L = net->styled[l];
-    sj.job[sj.n++] = StyleJob{L.mod_weight, L.mod_bias, F(pl.style_off[l]), L.cin, L.latent_row};
+    StyleJobs& d = (l <= n_first) ? sj[0] : sj[1];                // table l needs style l and style l + 1
+    d.job[d.n++] = StyleJob{L.mod_weight, L.mod_bias, F(pl.style_off[l]), L.cin, L.latent_row};
   }
   for (int r = 0; r < net->n_rgb; ++r) {
     const sgr_rgb_layer& R = net->rgb[r];
-    sj.job[sj.n++] = StyleJob{R.mod_weight, R.mod_bias, F(pl.rgbstyle_off[r]), R.cin, R.latent_row};
+    StyleJobs& d = (2 * r <= n_first) ? sj[0] : sj[1];            // ToRGB r hangs off styled layer 2r (layer 0 for r = 0)
+    d.job[d.n++] = StyleJob{R.mod_weight, R.mod_bias, F(pl.rgbstyle_off[r]), R.cin, R.latent_row};
   }
-  if (style_jobs_launch(sj, latent, latent_stride, batch, st)) return 1;
-
-  // 2. demodulation + epilogue tables (next layer's style, fused ToRGB coefficients)
-  TableJobs tj;
-  tj.n = net->n_styled;
+  TableJobs tj[2];
+  tj[0].n = tj[1].n = 0;
   for (int l = 0; l < net->n_styled; ++l) {
     const sgr_styled_layer& L = net->styled[l];
-    TableJob& j = tj.job[l];
+    TableJobs& d = l < n_first ? tj[0] : tj[1];
+    TableJob& j = d.job[d.n++];
     j.s = F(pl.style_off[l]);
     j.wsq = L.wsq;
     j.demod = F(pl.demod_off[l]);
@@ -440,7 +451,22 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
       return 1;
     }
   }
-  if (table_jobs_launch(tj, batch, st)) return 1;
+  if (style_jobs_launch(sj[0], latent, latent_stride, batch, st)) return 1;
+  bool prep_pending = false;
+  if (split_prep && sj[1].n + tj[1].n > 0) {
+    if (cudaEventRecord(tails->prep_fork, st) != cudaSuccess || cudaStreamWaitEvent(tails->side, tails->prep_fork, 0) != cudaSuccess) {
+      set_error("synthesis_forward: forking the side stream failed");
+      return 1;
+    }
+    if (sj[1].n > 0 && style_jobs_launch(sj[1], latent, latent_stride, batch, tails->side)) return 1;
+    if (tj[1].n > 0 && table_jobs_launch(tj[1], batch, tails->side)) return 1;
+    if (cudaEventRecord(tails->prep_join, tails->side) != cudaSuccess) {
+      set_error("synthesis_forward: side stream event failed");
+      return 1;
+    }
+    prep_pending = true;
+  }
+  if (table_jobs_launch(tj[0], batch, st)) return 1;
 
   // 3. modulated constant input
   int cur = 0;
@@ -449,7 +475,6 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
     return 1;
 
   // 4. the layer chain
-  TailStream* tails = g_prof_on ? nullptr : tail_stream();      // per-launch event timing keeps everything on one stream
   bool forked = false;
   int res = 4;
   int skip_cur = 0;
@@ -506,6 +531,14 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
       nx.single_pass = net->single_pass;
       nx.column_tile = net->styled[l + 1].column_tile;
       defer = halo_fusable(&nx);
+    }
+    if (prep_pending && l == n_first) {                      // the tables of layers >= kSplit come from the side stream
+      if (cudaStreamWaitEvent(st, tails->prep_join, 0) != cudaSuccess) {
+        set_error("synthesis_forward: joining the side stream failed");
+        return 1;
+      }
+      prep_pending = false;
+      forked = true;                                         // (the side stream has work of this call: join it at the end too)
     }
     g_prof_layer = l;
     const int rc_layer = modconv_forward_impl(&a, have_pending ? &pending_up : nullptr, defer, stream);
