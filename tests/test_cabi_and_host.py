@@ -159,3 +159,28 @@ def test_overlay_resolves_reference_imports():
     assert out[0] == 'stylegan_directions_face_reenactment_b200.model'
     assert out[1] == 'stylegan_directions_face_reenactment_b200.direction_matrix'
     assert out[2].startswith('/root/reference/')
+
+
+def test_sass_is_blackwell_native():
+    """The shipped library's GEMM kernels are tcgen05 / TMEM / TMA code (UTC*MMA, LDTM, UTMALDG / UBLKCP in SASS) and contain no
+    legacy mma.sync (HMMA): tools/sass_summary.py over libsgr.so (cuobjdump only, no GPU)."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'sass_summary.py')], capture_output=True, text=True, timeout=600).stdout
+    rows = {}
+    for ln in out.splitlines():
+        if ln.startswith('| `'):
+            c = [x.strip() for x in ln.strip().strip('|').split('|')]
+            rows.setdefault(c[0].strip('`').split('<')[0], []).append(c)
+    for k in ('modconv_halo_kernel', 'upconv_scatter_kernel', 'modconv_kernel', 'wgrad_kernel'):
+        assert k in rows, k
+        for c in rows[k]:
+            assert int(c[1]) > 0 and int(c[2]) > 0, (k, 'UTC*MMA / LDTM missing', c)          # tcgen05.mma, tcgen05.ld
+            assert int(c[4]) + int(c[6]) > 0, (k, 'no TMA loads', c)                           # UTMALDG or UBLKCP
+            assert int(c[10]) == 0, (k, 'legacy HMMA present', c)
+    total = [ln for ln in out.splitlines() if ln.startswith('| **total**')]
+    assert total and int(total[0].split('|')[11].strip()) == 0                               # no HMMA anywhere

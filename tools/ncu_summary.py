@@ -10,6 +10,7 @@ roofline.traffic)."""
 import collections
 import csv
 import json
+import re
 import subprocess
 import sys
 
@@ -56,7 +57,7 @@ def full(src, dst_md, dst_json):
     lines = []
     for r in data:
         vals = [r[i] for i in idx]
-        name = vals[0].replace('void sgr::', '').replace('sgr::', '').split('(')[0]
+        name = re.sub(r'\((int|bool|unsigned int)\)', '', vals[0]).replace('void sgr::', '').replace('sgr::', '').split('(')[0]
         rd, wr = float(vals[7].replace(',', '')), float(vals[8].replace(',', ''))
         if 'up_finish' in name:
             fin_bytes += (rd + wr) * 1e6
@@ -120,7 +121,7 @@ def hbm(src, dst_md, peak_gbs=None):
         f.write('| kernel | grid | us | DRAM rd MB | DRAM wr MB | GB/s | of peak | DRAM % (ncu) | SM % | sectors/req ld | sectors/req st | regs |\n')
         f.write('|---|---|---|---|---|---|---|---|---|---|---|---|\n')
         for r in data:
-            name = r[ci['Kernel Name']].replace('void sgr::', '').replace('sgr::', '').split('(')[0]
+            name = re.sub(r'\((int|bool|unsigned int)\)', '', r[ci['Kernel Name']]).replace('void sgr::', '').replace('sgr::', '').split('(')[0]
             us = num(r, 'gpu__time_duration.sum') * scale('gpu__time_duration.sum', time_u)
             rd = num(r, 'dram__bytes_read.sum') * scale('dram__bytes_read.sum', byte_u)
             wr = num(r, 'dram__bytes_write.sum') * scale('dram__bytes_write.sum', byte_u)
