@@ -16,21 +16,10 @@ import torch
 import torch.nn.functional as F
 
 from . import _native as N
-from .synthesis import _descriptor, _workspace
+from .synthesis import _descriptor, _workspace, synthesis_param_list  # noqa: F401  (re-exported)
 
 SQRT2 = math.sqrt(2.0)
 FORCE_ATEN_WGRAD = False      # tools/gpu_optimize_g_bench.py: time the ATen/cuDNN weight gradients against the library's
-
-
-def synthesis_param_list(g):
-    """The generator parameters the synthesis path reads, in a fixed order (the extra inputs of the autograd node)."""
-    ps = [g.input.input]
-    for layer in g.styled_layers():
-        ps += [layer.conv.weight, layer.conv.modulation.weight, layer.conv.modulation.bias, layer.noise.weight,
-               layer.activate.bias]
-    for layer in g.rgb_layers():
-        ps += [layer.conv.weight, layer.conv.modulation.weight, layer.conv.modulation.bias, layer.bias]
-    return ps
 
 
 def synthesis_backward(g, lat, feats, noise, grad_image, want_param_grads=False):

@@ -42,6 +42,14 @@ struct BwdActParams {
   float* ds_next;         // [B,C] += sum_p a * gx
   float* q;               // [B,C] += sum_p gt * (t - noise - bias)
   float* ds_rgb;          // [B,C] += sum_p a * sum_c grgb*wrgb/sqrt(C)
+  // PARAMS variant (generator-parameter gradients, optimize_g): per-channel sums of the same operands, formed in the
+  // same pass (they used to be a second kernel that re-read a and a stored fp32 copy of ga: 12 of 24 bytes per element)
+  //   d(activate.bias)[o] = sum_{b,p} gt        d(noise.weight) = sum_{b,o,p} gt * noise[p]
+  //   d(ToRGB.conv.weight)[c,o] = sum_{b,p} grgb[b,c,p] a[b,o,p] * s_rgb[b,o] / sqrt(C)      d(ToRGB.bias)[c] = sum_{b,p} grgb
+  float* g_act_bias;      // [C]
+  float* g_noise_w;       // [1]
+  float* g_wrgb;          // [3,C] or NULL
+  float* g_rgb_bias;      // [3]
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -54,8 +62,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (block stride), keeps the three per-(b,c) sums in registers, and the block issues ONE atomic per sum and channel at
 // the end (one warp-reduction + atomic per iteration put 1.6 M atomics on 1024 addresses at 256^2: 4x off the HBM time).
 constexpr int kBwdActThreads = 256;
-__global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdActParams p) {
-  __shared__ float red[kBwdActThreads / 32][24];
+template <bool PARAMS>
+__global__ void __launch_bounds__(kBwdActThreads, PARAMS ? 2 : 3) bwd_act_kernel(const BwdActParams p) {
+  constexpr int kSums = PARAMS ? 60 : 24;      // + 8 bias, 24 ToRGB weight, 3 ToRGB bias, 1 noise weight
+  __shared__ float red[kBwdActThreads / 32][kSums];
   const int HW = p.H * p.W;
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 8;
@@ -82,6 +92,14 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
   float dsn[8], qa[8], dsr[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) dsn[e] = qa[e] = dsr[e] = 0.f;
+  float gb[PARAMS ? 8 : 1], gw3[PARAMS ? 24 : 1], gb3[PARAMS ? 3 : 1], gnw = 0.f;
+  if (PARAMS) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gb[e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 24; ++e) gw3[e] = 0.f;
+    gb3[0] = gb3[1] = gb3[2] = 0.f;
+  }
 
   // one pixel per thread and iteration: consecutive lanes read consecutive floats of every channel plane (128 B per warp
   // and channel) and write consecutive 16 B operand chunks (4 pixels per thread made every store instruction touch
@@ -94,7 +112,13 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
 #pragma unroll
       for (int c = 0; c < 3; ++c) g3[c] = __ldg(p.grgb + (static_cast<size_t>(b) * 3 + c) * HW + pix);
     }
-    const float nz = p.noise ? nw * __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride + pix) : 0.f;
+    const float nraw = p.noise ? __ldg(p.noise + static_cast<size_t>(b) * p.noise_bstride + pix) : 0.f;
+    const float nz = nw * nraw;
+    if (PARAMS && p.grgb) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gb3[c] += g3[c];
+    }
+    float gtsum = 0.f;
     float av[8], gxv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -111,6 +135,10 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
         const float r = fmaf(g3[0], w0[e], fmaf(g3[1], w1[e], g3[2] * w2[e]));
         ga = fmaf(r, sr[e], ga);
         dsr[e] = fmaf(a, r, dsr[e]);
+        if (PARAMS) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gw3[c * 8 + e] = fmaf(a, g3[c], gw3[c * 8 + e]);
+        }
       }
       if (p.out_ga) p.out_ga[(static_cast<size_t>(b) * p.C + c0 + e) * HW + pix] = ga;
       gzv[e] = 0.f;
@@ -120,8 +148,13 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
         const float t = pos ? a * kInvSqrt2 : a * (5.f * kInvSqrt2);
         qa[e] = fmaf(gt, t - nz - bi[e], qa[e]);
         gzv[e] = gt * dm[e];
+        if (PARAMS) {
+          gb[e] += gt;
+          gtsum += gt;
+        }
       }
     }
+    if (PARAMS) gnw = fmaf(gtsum, nraw, gnw);
     if (p.out_gz4 && p.act) {
       float* dst = p.out_gz4 + ((static_cast<size_t>(b) * (p.C / 4) + blockIdx.y * 2) * HW + pix) * 4;
       *reinterpret_cast<float4*>(dst) = make_float4(gzv[0], gzv[1], gzv[2], gzv[3]);
@@ -155,6 +188,17 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
     qa[e] = warp_sum(qa[e]);
     dsr[e] = warp_sum(dsr[e]);
   }
+  if (PARAMS) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gb[e] = warp_sum(gb[e]);
+    if (p.grgb) {
+#pragma unroll
+      for (int e = 0; e < 24; ++e) gw3[e] = warp_sum(gw3[e]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gb3[c] = warp_sum(gb3[c]);
+    }
+    gnw = warp_sum(gnw);
+  }
   if (lane == 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -162,17 +206,40 @@ __global__ void __launch_bounds__(kBwdActThreads, 3) bwd_act_kernel(const BwdAct
       red[warp][8 + e] = qa[e];
       red[warp][16 + e] = dsr[e];
     }
+    if (PARAMS) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][24 + e] = gb[e];
+#pragma unroll
+      for (int e = 0; e < 24; ++e) red[warp][32 + e] = gw3[e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) red[warp][56 + c] = gb3[c];
+      red[warp][59] = gnw;
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 24) {
+  if (threadIdx.x < kSums) {
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < kBwdActThreads / 32; ++w) v += red[w][threadIdx.x];
-    const int kind = threadIdx.x >> 3, e = threadIdx.x & 7;
-    const size_t o = static_cast<size_t>(b) * p.C + c0 + e;
-    if (kind == 0 && p.ds_next && p.gx) atomicAdd(p.ds_next + o, v);
-    if (kind == 1 && p.act) atomicAdd(p.q + o, v);
-    if (kind == 2 && p.grgb) atomicAdd(p.ds_rgb + o, v);
+    const int k = threadIdx.x;
+    if (k < 24) {
+      const int kind = k >> 3, e = k & 7;
+      const size_t o = static_cast<size_t>(b) * p.C + c0 + e;
+      if (kind == 0 && p.ds_next && p.gx) atomicAdd(p.ds_next + o, v);
+      if (kind == 1 && p.act) atomicAdd(p.q + o, v);
+      if (kind == 2 && p.grgb) atomicAdd(p.ds_rgb + o, v);
+    } else if (PARAMS && p.act) {
+      if (k < 32) {
+        atomicAdd(p.g_act_bias + c0 + (k - 24), v);
+      } else if (k < 56) {
+        const int c = (k - 32) >> 3, e = (k - 32) & 7;
+        if (p.grgb && p.g_wrgb) atomicAdd(p.g_wrgb + c * p.C + c0 + e, v * sr[e] * rs);
+      } else if (k < 59) {
+        if (p.grgb && p.g_rgb_bias && blockIdx.y == 0) atomicAdd(p.g_rgb_bias + (k - 56), v);
+      } else if (p.noise) {
+        atomicAdd(p.g_noise_w, v);
+      }
+    }
   }
 }
 
@@ -185,7 +252,8 @@ static int bwd_act_launch(BwdActParams p, cudaStream_t st) {
   while (iters < 16 && (groups / (iters * 2)) * others >= 2048) iters *= 2;
   p.iters = iters;
   dim3 grid((groups + iters - 1) / iters, p.C / 8, p.B);
-  bwd_act_kernel<<<grid, kBwdActThreads, 0, st>>>(p);
+  if (p.g_act_bias) bwd_act_kernel<true><<<grid, kBwdActThreads, 0, st>>>(p);
+  else bwd_act_kernel<false><<<grid, kBwdActThreads, 0, st>>>(p);
   count_launch();
   return check_launch("bwd_act_kernel") ? 0 : 1;
 }
@@ -312,73 +380,14 @@ __global__ void dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, 
             acc * 0.044194173824159216f);
 }
 
-
-// ------------------------------------------------------------------------------------------------------------------
-// Generator-parameter gradients (train() mode, optimize_g: libs/optimization.py:25-72).
-// Per styled layer, from the saved output a and its gradient ga (gt = ga * sqrt2 * (a > 0 ? 1 : 0.2)):
-//   d(activate.bias)[o] = sum_{b,p} gt           d(noise.weight) = sum_{b,o,p} gt * noise[b?,p]
-//   d(ToRGB.conv.weight)[c,o] = sum_{b,p} grgb[b,c,p] a[b,o,p] * s_rgb[b,o] / sqrt(C)      d(ToRGB.bias)[c] = sum_{b,p} grgb
-// grid (C, B, pixel spans): a block walks its span of one (channel, sample) plane; block reduction, one atomic per sum.
-struct ParamSumsParams {
-  int B, C, HW;
-  const float* a;
-  long long a_bstride;
-  const float* ga;            // [B,C,HW]
-  const float* noise;         // [HW] (+ batch stride) or NULL
-  long long noise_bstride;
-  const float* grgb;          // [B,3,HW] or NULL
-  const float* s_rgb;         // [B,C]
-  float* g_act_bias;          // [C]
-  float* g_noise_w;           // [1]
-  float* g_wrgb;              // [3,C]
-  float* g_rgb_bias;          // [3]
+struct ZeroJobs {
+  float* ptr[2 * (SGR_MAX_STYLED + SGR_MAX_RGB)];
+  int count[2 * (SGR_MAX_STYLED + SGR_MAX_RGB)];
+  int n;
 };
-
-__global__ void __launch_bounds__(256) param_sums_kernel(const ParamSumsParams p) {
-  __shared__ float red[8][8];
-  const int c = blockIdx.x, b = blockIdx.y;
-  const float kSqrt2 = 1.4142135623730951f;
-  const float* a = p.a + static_cast<size_t>(b) * p.a_bstride + static_cast<size_t>(c) * p.HW;
-  const float* ga = p.ga + (static_cast<size_t>(b) * p.C + c) * p.HW;
-  const float* nz = p.noise ? p.noise + static_cast<size_t>(b) * p.noise_bstride : nullptr;
-  const float* g3 = p.grgb ? p.grgb + static_cast<size_t>(b) * 3 * p.HW : nullptr;
-  float v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = 0.f;
-  const int span = (p.HW + gridDim.z - 1) / gridDim.z;
-  const int pix_end = min(p.HW, static_cast<int>(blockIdx.z + 1) * span);
-  for (int pix = blockIdx.z * span + threadIdx.x; pix < pix_end; pix += blockDim.x) {
-    const float av = __ldg(a + pix);
-    const float gt = __ldg(ga + pix) * (av > 0.f ? kSqrt2 : 0.2f * kSqrt2);
-    v[0] += gt;
-    if (nz) v[1] = fmaf(gt, __ldg(nz + pix), v[1]);
-    if (g3) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float g = __ldg(g3 + static_cast<size_t>(k) * p.HW + pix);
-        v[2 + k] = fmaf(av, g, v[2 + k]);
-        v[5 + k] += g;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = warp_sum(v[k]);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) red[warp][k] = v[k];
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    const int k = threadIdx.x;
-    if (k == 0) atomicAdd(p.g_act_bias + c, t);
-    if (k == 1 && nz) atomicAdd(p.g_noise_w, t);
-    if (k >= 2 && k < 5 && g3)
-      atomicAdd(p.g_wrgb + (k - 2) * p.C + c, t * __ldg(p.s_rgb + static_cast<size_t>(b) * p.C + c) * rsqrtf(static_cast<float>(p.C)));
-    if (k >= 5 && g3 && c == 0) atomicAdd(p.g_rgb_bias + (k - 5), t);
-  }
+__global__ void zero_jobs_kernel(const ZeroJobs jobs) {
+  float* p = jobs.ptr[blockIdx.x];
+  for (int i = threadIdx.x; i < jobs.count[blockIdx.x]; i += blockDim.x) p[i] = 0.f;
 }
 
 // d(modulation.weight)[i,k] = sum_b ds[b,i] * latent[b,row,k] / sqrt(512),  d(modulation.bias)[i] = sum_b ds[b,i]
@@ -500,7 +509,7 @@ using namespace sgr;
 extern "C" {
 
 // caller-allocated scratch of the parameter-gradient path:
-//   [modulated layer input as a C8 operand | dL/d(layer output) fp32 | slice partials of the weight-gradient GEMM]
+//   [modulated layer input as a C8 operand | slice partials of the weight-gradient GEMM]
 static size_t wgrad_xs_bytes(const sgr_synthesis* net, int batch) {
   size_t max_in = 0;
   for (int l = 0; l < net->n_styled; ++l) {
@@ -510,20 +519,12 @@ static size_t wgrad_xs_bytes(const sgr_synthesis* net, int batch) {
   }
   return align_up(max_in * 4, 256);
 }
-static size_t wgrad_ga_bytes(const sgr_synthesis* net, int batch) {
-  size_t max_out = 0;
-  for (int l = 0; l < net->n_styled; ++l) {
-    const size_t res_out = static_cast<size_t>(4) << ((l + 1) / 2);
-    max_out = std::max(max_out, static_cast<size_t>(batch) * net->styled[l].cout * res_out * res_out);
-  }
-  return align_up(max_out * 4, 256);
-}
 
 size_t sgr_synthesis_wgrad_scratch_bytes(const sgr_synthesis* net, int batch) {
   if (!net || batch <= 0 || net->n_styled < 1 || net->n_styled > SGR_MAX_STYLED) return 0;
   size_t part = 0;
   for (int l = 0; l < net->n_styled; ++l) part = std::max(part, wgrad_scratch_bytes(net->styled[l].cout, net->styled[l].cin));
-  return wgrad_xs_bytes(net, batch) + wgrad_ga_bytes(net, batch) + align_up(part, 256);
+  return wgrad_xs_bytes(net, batch) + align_up(part, 256);
 }
 
 size_t sgr_synthesis_backward_workspace_bytes(const sgr_synthesis* net, int batch) {
@@ -565,7 +566,7 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
   const int latent_stride = net->n_latent * SGR_STYLE_DIM;
   const int L = net->n_styled, R = net->n_rgb;
   const sgr_param_grads* pg = extras ? extras->params : nullptr;
-  const size_t xs_bytes = wgrad_xs_bytes(net, batch), ga_bytes = wgrad_ga_bytes(net, batch);
+  const size_t xs_bytes = wgrad_xs_bytes(net, batch);
   if (pg) {
     if (!extras->wgrad_scratch || (reinterpret_cast<uintptr_t>(extras->wgrad_scratch) & 255) != 0 ||
         extras->wgrad_scratch_bytes < sgr_synthesis_wgrad_scratch_bytes(net, batch)) {
@@ -587,19 +588,21 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
       set_error("synthesis_backward: sgr_param_grads has a null pointer, or a layer is packed in polyphase mode (up == 1)");
       return 1;
     }
-    for (int l = 0; l < net->n_styled; ++l)
-      if (cudaMemsetAsync(pg->styled[l].g_noise_weight, 0, 4, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
-          cudaMemsetAsync(pg->styled[l].g_act_bias, 0, static_cast<size_t>(net->styled[l].cout) * 4,
-                          static_cast<cudaStream_t>(stream)) != cudaSuccess) {
-        set_error("synthesis_backward: memset failed");
-        return 1;
-      }
-    for (int r = 0; r < net->n_rgb; ++r)
-      if (cudaMemsetAsync(pg->rgb[r].g_weight, 0, static_cast<size_t>(net->rgb[r].cin) * 12, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
-          cudaMemsetAsync(pg->rgb[r].g_bias, 0, 12, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
-        set_error("synthesis_backward: memset failed");
-        return 1;
-      }
+    // the atomically accumulated sums start from zero: one launch for all of them (40 memsets cost 0.1 ms of host time,
+    // which a batch-1 optimize_g step is bound by)
+    ZeroJobs zj;
+    zj.n = 0;
+    for (int l = 0; l < net->n_styled; ++l) {
+      zj.ptr[zj.n] = pg->styled[l].g_noise_weight; zj.count[zj.n++] = 1;
+      zj.ptr[zj.n] = pg->styled[l].g_act_bias; zj.count[zj.n++] = net->styled[l].cout;
+    }
+    for (int r = 0; r < net->n_rgb; ++r) {
+      zj.ptr[zj.n] = pg->rgb[r].g_weight; zj.count[zj.n++] = net->rgb[r].cin * 3;
+      zj.ptr[zj.n] = pg->rgb[r].g_bias; zj.count[zj.n++] = 3;
+    }
+    zero_jobs_kernel<<<zj.n, 128, 0, static_cast<cudaStream_t>(stream)>>>(zj);
+    count_launch();
+    if (!check_launch("zero_jobs_kernel")) return 1;
   }
 
   // styles + demod (recomputed: cheaper than keeping them alive between forward and backward)
@@ -675,7 +678,14 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
     p.noise_bstride = Ly.noise_batch_stride;
     p.noise_w = Ly.noise_weight;
     if (extras && extras->gfeats) p.out_ga = extras->gfeats[l];
-    if (pg && !p.out_ga) p.out_ga = reinterpret_cast<float*>(static_cast<char*>(extras->wgrad_scratch) + xs_bytes);
+    if (pg) {      // per-channel parameter sums ride on this pass (bwd_act_kernel<true>)
+      p.g_act_bias = pg->styled[l].g_act_bias;
+      p.g_noise_w = pg->styled[l].g_noise_weight;
+      if (!Ly.up) {
+        p.g_wrgb = pg->rgb[r].g_weight;
+        p.g_rgb_bias = pg->rgb[r].g_bias;
+      }
+    }
     const bool scatter = Ly.up == 2;      // gather adjoint: FIR^T to parity planes, then the 9 real taps
     if (scatter) p.out_gz4 = F(pl.gz_off);
     else p.out_c8 = reinterpret_cast<__nv_bfloat16*>(ws + pl.gz_off);
@@ -704,24 +714,9 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
       count_launch();
       if (!check_launch("up_bwd_prepare_kernel")) return 1;
     }
-    // generator-parameter gradients (optimize_g): per-channel sums, then the weight-gradient GEMM of the gz operand just
-    // built x the modulated layer input, re-split from the saved fp32 activation of the previous layer (conv1: the constant)
+    // generator-parameter gradients (optimize_g): the weight-gradient GEMM of the gz operand just built x the modulated
+    // layer input, re-split from the saved fp32 activation of the previous layer (conv1: the constant)
     if (pg) {
-      ParamSumsParams sp;
-      memset(&sp, 0, sizeof(sp));
-      sp.B = batch; sp.C = Ly.cout; sp.HW = res_out * res_out;
-      sp.a = feats[l]; sp.a_bstride = p.a_bstride; sp.ga = p.out_ga;
-      sp.noise = Ly.noise; sp.noise_bstride = Ly.noise_batch_stride;
-      if (!Ly.up) {
-        sp.grgb = grgb[r]; sp.s_rgb = F(pl.rgbstyle_off[r]);
-        sp.g_wrgb = pg->rgb[r].g_weight; sp.g_rgb_bias = pg->rgb[r].g_bias;
-      }
-      sp.g_act_bias = pg->styled[l].g_act_bias; sp.g_noise_w = pg->styled[l].g_noise_weight;
-      const int spans = std::max(1, std::min(32, sp.HW / 2048));      // >= 2048 pixels per block, enough blocks at batch 1
-      param_sums_kernel<<<dim3(Ly.cout, batch, spans), 256, 0, st>>>(sp);
-      count_launch();
-      if (!check_launch("param_sums_kernel")) return 1;
-
       char* xs = static_cast<char*>(extras->wgrad_scratch);
       if (l == 0) {
         if (const_input_launch(net->const_input, F(pl.style_off[0]), batch, Ly.cin, SGR_FMT_BF16, xs, st)) return 1;
@@ -735,8 +730,8 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
       wa.x_c8 = xs;
       wa.gz_c8 = scatter ? ws + pl.planes_off : ws + pl.gz_off;
       wa.gw = pg->styled[l].g_weight;
-      wa.scratch = xs + xs_bytes + ga_bytes;
-      wa.scratch_bytes = extras->wgrad_scratch_bytes - xs_bytes - ga_bytes;
+      wa.scratch = xs + xs_bytes;
+      wa.scratch_bytes = extras->wgrad_scratch_bytes - xs_bytes;
       WgradFinish wf;
       wf.weight = pg->styled[l].weight; wf.q = F(pl.q_off[l]); wf.demod = F(pl.demod_off[l]); wf.style = F(pl.style_off[l]);
       wf.batch = batch; wf.scale = 1.f / sqrtf(static_cast<float>(Ly.cin) * 9.f);

@@ -144,39 +144,52 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
+    // The issuing thread is the limiter once the operands are resident (about 8 cycles per instruction, DESIGN.md
+    // section 4): the four descriptors of a K step differ only in their 14-bit start-address field, so they are built once
+    // per launch and advanced with 32-bit adds on the low word (16-byte units) — 4 adds + 3 MMAs per K step.
     if (elect_one_sync()) {
       const uint32_t idesc = wg_idesc(p.nt);
-      const uint32_t a_plane = 16 * p.a_sbo;                       // 16 chunks per plane of the gz box
-      const uint32_t b_sbo = kWgPix * 16, b_plane = (p.nt / 8) * b_sbo;
-      uint32_t it = 0, icount = 0;
+      const uint32_t b_sbo = kWgPix * 16;
+      const uint64_t a_d0 = umma_desc(smem_u32(stage_base), p.a_lbo, p.a_sbo);
+      const uint64_t b_d0 = umma_desc(smem_u32(stage_base) + p.a_bytes, 128, b_sbo);
+      const uint32_t a_hiw = static_cast<uint32_t>(a_d0 >> 32), b_hiw = static_cast<uint32_t>(b_d0 >> 32);
+      const uint32_t a_low0 = static_cast<uint32_t>(a_d0), b_low0 = static_cast<uint32_t>(b_d0);
+      const uint32_t stage16 = stage_bytes >> 4;
+      const uint32_t a_plane16 = p.a_sbo;                          // 16 chunks per plane of the gz box: 16 * a_sbo bytes
+      const uint32_t b_plane16 = static_cast<uint32_t>(p.nt / 8) * (b_sbo >> 4);
+      const uint32_t a_k16 = p.a_kstep >> 4;
+      auto desc = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      uint32_t s = 0, phase = 0, icount = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++icount) {
         const WgItem w = wg_decode(p, item);
         const WgradGroup& G = p.g[w.g];
+        const int ntaps = G.ntaps;
         mbar_wait(tempty, (icount & 1) ^ 1);
         tc_fence_after();
-        for (int pt = w.p0; pt < w.p1; ++pt, ++it) {
-          const uint32_t s = it % S;
-          mbar_wait(&full[s], (it / S) & 1);
+        for (int pt = w.p0; pt < w.p1; ++pt) {
+          mbar_wait(&full[s], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + s * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_bytes;
+          const uint32_t a_s = a_low0 + s * stage16, b_s = b_low0 + s * stage16;
+          const uint32_t acc0 = pt > w.p0 ? 1u : 0u;
 #pragma unroll 1
-          for (int t = 0; t < G.ntaps; ++t) {
+          for (int t = 0; t < ntaps; ++t) {
             const uint32_t d_tmem = tmem_base + t * p.nt;
+            uint32_t a_hi = a_s + (static_cast<uint32_t>(G.tap_off[t]) >> 4), b_hi = b_s;
 #pragma unroll
             for (int j = 0; j < kWgPix / 16; ++j) {
-              const uint32_t a_off = a_addr + G.tap_off[t] + j * p.a_kstep;
-              const uint32_t b_off = b_addr + j * 256;
-              const uint64_t a_hi = umma_desc(a_off, p.a_lbo, p.a_sbo);
-              const uint64_t a_lo = umma_desc(a_off + a_plane, p.a_lbo, p.a_sbo);
-              const uint64_t b_hi = umma_desc(b_off, 128, b_sbo);
-              const uint64_t b_lo = umma_desc(b_off + b_plane, 128, b_sbo);
-              umma_bf16(d_tmem, a_lo, b_hi, idesc, (pt > w.p0 || j > 0) ? 1u : 0u);
-              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1);
+              const uint32_t a_lo = a_hi + a_plane16, b_lo = b_hi + b_plane16;
+              umma_bf16(d_tmem, desc(a_hiw, a_lo), desc(b_hiw, b_hi), idesc, j > 0 ? 1u : acc0);
+              umma_bf16(d_tmem, desc(a_hiw, a_hi), desc(b_hiw, b_lo), idesc, 1);
+              umma_bf16(d_tmem, desc(a_hiw, a_hi), desc(b_hiw, b_hi), idesc, 1);
+              a_hi += a_k16;
+              b_hi += 16;                                          // 256 bytes: the next two 8-pixel groups of the xs tile
             }
           }
           umma_commit(&empty[s]);
+          if (++s == static_cast<uint32_t>(S)) {
+            s = 0;
+            phase ^= 1;
+          }
         }
         umma_commit(tfull);
       }

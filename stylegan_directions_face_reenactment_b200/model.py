@@ -173,16 +173,29 @@ class ModulatedConv2d(nn.Module):
         return cache['fir_mode']
 
     def packed(self, transpose=False, fmt=None, nt=0):
-        """(w_packed, wsq) device tensors for the tcgen05 kernel; repacked when the parameter changes.
+        """(w_packed, wsq) device tensors for the tcgen05 kernel; refilled when the parameter changes.
         The adjoint (transpose) is always packed as bf16 hi/lo: it multiplies gradients (csrc/backward.cu).
-        `nt` is the GEMM column tile the layout is built for (0 = library default, see sgr_choose_column_tile)."""
+        `nt` is the GEMM column tile the layout is built for (0 = library default, see sgr_choose_column_tile).
+        An in-place update of the weight (an optimizer step: same storage, new version) refills every cached variant in its
+        existing buffer, so the C descriptors and captured graphs that point at them stay valid (optimize_g,
+        libs/optimization.py:45-68: one Adam step per forward); a new storage drops the cache."""
         w = self.weight
         fir = self.blur.kernel if self.upsample else None
         fmt = N.FMT_BF16 if transpose else (N.default_format() if fmt is None else fmt)
         version = _version_key(*([w] + ([fir] if fir is not None else [])))
-        if self._pack_cache.get('version') != version:          # parameter changed: every packed variant is stale
-            self._pack_cache.clear()
-            self._pack_cache['version'] = version
+        cache = self._pack_cache
+        old = cache.get('version')
+        if old != version:
+            in_place = (old is not None and len(old) == len(version) and old[1:] == version[1:] and
+                        old[0][0] == version[0][0] and old[0][2] == version[0][2] and len(cache) <= 7)
+            # (only the weight's version moved; a cache that has collected many layouts is dropped instead of refilled)
+            if in_place:
+                cache['version'] = version
+                for slot, (packed, wsq) in [(k, v) for k, v in cache.items() if k != 'version']:
+                    self._fill_packed(slot, packed, wsq)
+            else:                                                # new storage / new FIR: every packed variant is stale
+                cache.clear()
+                cache['version'] = version
         # upsampling layers: forward operator in scatter form (up=2: 9 real taps + FIR pass), adjoint in polyphase form
         # (up=2: forward = 9-tap scatter conv + FIR pass, adjoint = FIR^T to parity planes + 9-tap gather conv; up=1: both
         # in polyphase form, for a blur kernel that is not an outer product)
@@ -190,28 +203,43 @@ class ModulatedConv2d(nn.Module):
         if up_mode == 2 and not transpose:
             nt = 0                                               # fixed by the scatter layout
         slot = (bool(transpose), fmt, nt, up_mode)
-        hit = self._pack_cache.get(slot)
+        hit = cache.get(slot)
         if hit is not None:
             return hit
+        cout, cin = self._packed_dims(transpose)
+        nbytes = N.lib().sgr_packed_weight_bytes(cout, cin, self.kernel_size, up_mode, int(transpose))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if not transpose else None
+        self._fill_packed(slot, packed, wsq)
+        cache[slot] = (packed, wsq)
+        return packed, wsq
+
+    def _packed_dims(self, transpose):
+        cout, cin = self.out_channel, self.in_channel
+        if not transpose and cout < 32:                          # ToRGB (3 channels): the GEMM columns are padded to 32
+            cout = 32
+        if cin % 32:                                             # zero input channels up to the K granularity
+            cin += 32 - cin % 32
+        return cout, cin
+
+    def _fill_packed(self, slot, packed, wsq):
+        transpose, fmt, nt, up_mode = slot
         cout, cin, ks = self.out_channel, self.in_channel, self.kernel_size
-        wd = w.detach()
-        if not transpose and cout < 32:                      # ToRGB (3 channels): pad the GEMM columns to 32
+        wd = self.weight.detach()
+        if not transpose and cout < 32:
             wd = torch.cat([wd[0], wd.new_zeros(32 - cout, cin, ks, ks)], 0)
             cout = 32
         wd = wd.reshape(cout, cin, ks, ks)
-        if cin % 32:                                         # zero input channels up to the K granularity
+        if cin % 32:
             wd = torch.cat([wd, wd.new_zeros(cout, 32 - cin % 32, ks, ks)], 1) * math.sqrt((cin + 32 - cin % 32) / cin)
-            cin = wd.shape[1]                                # (the factor undoes the 1/sqrt(cin k^2) of the padded cin)
-        wd = wd.contiguous().float()
-        lib = N.lib()
-        nbytes = lib.sgr_packed_weight_bytes(cout, cin, ks, up_mode, int(transpose))
-        packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        wsq = torch.empty(cout, cin, dtype=torch.float32, device=w.device) if not transpose else None
+            cin = wd.shape[1]                                    # (the factor undoes the 1/sqrt(cin k^2) of the padded cin)
+        if wd.dtype != torch.float32 or not wd.is_contiguous():
+            wd = wd.contiguous().float()
+        fir = self.blur.kernel if self.upsample else None
         firc = None if fir is None else fir.detach().contiguous().float()
-        N.check(lib.sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, up_mode, int(transpose),
-                                            fmt, nt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
-        self._pack_cache[slot] = (packed, wsq)
-        return packed, wsq
+        with torch.cuda.device(wd.device):
+            N.check(N.lib().sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, up_mode, int(transpose),
+                                                    fmt, nt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
 
     def forward(self, input, style):
         """Module-level call on NCHW fp32 tensors (the fused Generator.forward never goes through here)."""

@@ -21,6 +21,8 @@ class NetDescriptor:
     def __init__(self, g, noise, batch, backward=False):
         self.keep = []
         self.noise_used = []
+        self.copied = False                            # a tensor had to be converted: the struct points at a snapshot
+        self.pack_calls = []                           # (conv, kwargs, struct field, pointer) of every packed operand
         s = N.Synthesis()
         styled = g.styled_layers()
         rgbs = g.rgb_layers()
@@ -39,12 +41,17 @@ class NetDescriptor:
                 d.fir = self._p(conv.blur.kernel)
             else:                                      # plain layers, or polyphase fallback for a non-separable FIR
                 d.column_tile = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.out_channel * (4 if d.up else 1))
-            packed, wsq = conv.packed(fmt=s.format, nt=d.column_tile)
+            kw = dict(fmt=s.format, nt=d.column_tile)
+            packed, wsq = conv.packed(**kw)
             d.latent_row = 0 if l == 0 else l          # conv1 <- row 0, convs[j] <- row j+1 (model.py:520-531)
             d.w_packed, d.wsq = self._p(packed), self._p(wsq)
+            self.pack_calls.append((conv, kw, packed.data_ptr()))
             if backward:
                 d.column_tile_t = N.lib().sgr_choose_column_tile(batch, res_in, res_in, conv.in_channel)
-                d.w_packed_t = self._p(conv.packed(transpose=True, nt=d.column_tile_t)[0])
+                kw = dict(transpose=True, nt=d.column_tile_t)
+                packed_t = conv.packed(**kw)[0]
+                d.w_packed_t = self._p(packed_t)
+                self.pack_calls.append((conv, kw, packed_t.data_ptr()))
             d.mod_weight, d.mod_bias = self._p(conv.modulation.weight), self._p(conv.modulation.bias)
             nz = noise[l]
             res = 4 << ((l + 1) // 2)
@@ -66,39 +73,80 @@ class NetDescriptor:
             d.bias = self._p(layer.bias)
             d.fir = self._p(layer.upsample.kernel) if hasattr(layer, 'upsample') else None
             if backward and hasattr(layer, 'upsample'):
-                d.fir_flipped = self._p(torch.flip(layer.upsample.kernel, [0, 1]))
+                d.fir_flipped = self._p(_flipped_fir(layer.upsample))
         self.struct = s
 
     def _p(self, t):
-        t = _f32c(t) if t.dtype != torch.uint8 else t
+        if t.dtype != torch.uint8:
+            c = _f32c(t)
+            if c.data_ptr() != t.data_ptr():
+                self.copied = True
+            t = c
         self.keep.append(t)
         return N.ptr(t)
 
+    def refresh(self):
+        """After an in-place parameter update (optimizer step: same storages, new versions): the struct points straight at
+        the parameters, so only the packed tensor-core weights are stale — ModulatedConv2d.packed refills them in their
+        existing buffers.  False = something moved, build a new descriptor."""
+        if self.copied:
+            return False
+        for conv, kw, ptr in self.pack_calls:
+            if conv.packed(**kw)[0].data_ptr() != ptr:
+                return False
+        return True
+
+
+def _flipped_fir(upsample):
+    """flip(kernel) of a ToRGB skip upsampler (operand of the adjoint upfirdn2d, op/upfirdn2d.py:112-117), cached per buffer
+    version."""
+    k = upsample.kernel
+    key = (k.data_ptr(), k._version)
+    hit = upsample.__dict__.get('_flipped')
+    if hit is None or hit[0] != key:
+        hit = upsample.__dict__['_flipped'] = (key, torch.flip(k.detach(), [0, 1]).contiguous().float())
+    return hit[1]
+
+
+def synthesis_param_list(g):
+    """The generator parameters the synthesis path reads, in a fixed order (the extra inputs of the autograd node)."""
+    ps = [g.input.input]
+    for layer in g.styled_layers():
+        ps += [layer.conv.weight, layer.conv.modulation.weight, layer.conv.modulation.bias, layer.noise.weight,
+               layer.activate.bias]
+    for layer in g.rgb_layers():
+        ps += [layer.conv.weight, layer.conv.modulation.weight, layer.conv.modulation.bias, layer.bias]
+    return ps
+
 
 def _signature(g):
-    """(data_ptr, version) of every parameter and buffer the descriptor points at: detects in-place updates (Adam in
-    optimize_g), load_state_dict, .cuda() and re-assignment."""
-    sig = []
-    for t in g.parameters():
-        sig.append(t.data_ptr())
-        sig.append(t._version)
-    for t in g.buffers():
-        sig.append(t.data_ptr())
-        sig.append(t._version)
-    return tuple(sig)
+    """((data_ptr...), (version...)) of every parameter, and the same of every buffer, the descriptor points at: detects
+    in-place updates (Adam in optimize_g), load_state_dict, .cuda() and re-assignment.  Only the synthesis network's own
+    tensors are walked (a module-tree walk costs 0.2 ms: as much as the kernels of a batch-1 frame take to launch)."""
+    ps = synthesis_param_list(g)
+    bufs = [layer.conv.blur.kernel for layer in g.styled_layers() if layer.conv.upsample]
+    bufs += [layer.upsample.kernel for layer in g.rgb_layers() if hasattr(layer, 'upsample')]
+    return (tuple([t.data_ptr() for t in ps]), tuple([t._version for t in ps]), ps[0].device.index,
+            tuple([t.data_ptr() for t in bufs]), tuple([t._version for t in bufs]))
 
 
 def _descriptor(g, noise, batch, backward=False):
     """NetDescriptor for this call, reused from the previous call when nothing it points at has changed (building it is
-    ~0.25 ms of Python: the dominant cost of a batch-1 frame, which is how run_inference.py drives the generator)."""
+    ~0.25 ms of Python: the dominant cost of a batch-1 frame, which is how run_inference.py drives the generator), and
+    refreshed in place when only parameter versions moved (an optimizer step between two calls)."""
     if any(n is None for n in noise):                  # randomize_noise: fresh tensors every call
         return NetDescriptor(g, noise, batch, backward)
     key = (batch, backward, N.default_format(), N.single_pass(), tuple((n.data_ptr(), n._version, tuple(n.shape)) for n in noise))
     sig = _signature(g)
     cache = g.__dict__.setdefault('_desc_cache', {})
     hit = cache.get(key)
-    if hit is not None and hit[0] == sig:
-        return hit[1]
+    if hit is not None:
+        if hit[0] == sig:
+            return hit[1]
+        old = hit[0]
+        if old[0] == sig[0] and old[2:] == sig[2:] and hit[1].refresh():      # same storages, same buffers
+            cache[key] = (sig, hit[1])
+            return hit[1]
     desc = NetDescriptor(g, noise, batch, backward)
     desc.keep.extend(noise)                            # the cached struct points at them
     if len(cache) >= 8:
@@ -263,7 +311,6 @@ def run_synthesis(g, latent, noise, return_features=False):
         #   'always'          exactly the reference: formed whenever any synthesis parameter requires grad.
         #   'never'           latent gradient only.
         # Freezing the generator (G.requires_grad_(False)) selects the latent-only path without any warning.
-        from .backward import synthesis_param_list
         params = synthesis_param_list(g)
         mode = getattr(g, 'param_grads', 'auto')
         if mode not in ('auto', 'always', 'never'):

@@ -803,3 +803,23 @@ def test_optimize_g_style_finetuning_step_reduces_loss(pkg):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < 0.9 * losses[0] and all(np.isfinite(losses)), losses
+    # Adam updates the weights in place: the cached C descriptors are refreshed (packed tensor-core operands refilled in
+    # their buffers), not rebuilt and never stale — a generator rebuilt from the state_dict renders the same frame bit for bit
+    cache = G.__dict__['_desc_cache']
+    before = {k: id(v[1]) for k, v in cache.items()}
+    assert len(before) == 2                                          # one forward, one backward descriptor
+    img, _ = G([latent], input_is_latent=True)
+    img.square().mean().backward()
+    assert {k: id(v[1]) for k, v in cache.items()} == before
+    G2 = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G2.load_state_dict({k: v.detach().cpu() for k, v in G.state_dict().items()}, strict=True)
+    G2 = G2.cuda().train()
+    img2, _ = G2([latent], input_is_latent=True)
+    assert torch.equal(img.detach(), img2.detach())
+    G.zero_grad(set_to_none=True)
+    img, _ = G([latent], input_is_latent=True)
+    img.square().mean().backward()
+    img2.square().mean().backward()
+    for (n, p), p2 in zip(G.named_parameters(), G2.parameters()):
+        if p.grad is not None:
+            assert torch.allclose(p.grad, p2.grad, rtol=1e-4, atol=1e-6 * float(p2.grad.abs().max())), n
