@@ -33,8 +33,12 @@ struct ScatterCfg {
   static constexpr int kAStages = 4;                                      // one slot per shift: slot index == shift
   static constexpr int kHaloStages = 3;                                   // wrapped-halo tiles: ring of channel blocks in the same 64 KiB
   static constexpr int kHaloStageBytes = 8 * 144 * 16 + 2304;             // 8 chunk-planes of <= 144 box entries + the over-read of the last one
-  static constexpr int kStageOff = 1024 + kAStages * kABytes + kGroups * kGroupBytes;
-  static constexpr int kSmemBytes = kStageOff + 8 * kTileM * 16;          // + epilogue staging: 8 channel groups x 128 pixels x 16 B
+  // [barriers | A ring | epilogue staging (8 channel groups x 128 pixels x 16 B) | B ring]; linear tiles store per lane and
+  // use the staging area as part of their A ring
+  static constexpr int kStageOff = 1024 + kAStages * kABytes;
+  static constexpr int kARegion = kAStages * kABytes + 8 * kTileM * 16;
+  static constexpr int kBOff = 1024 + kARegion;
+  static constexpr int kSmemBytes = kBOff + kGroups * kGroupBytes;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory");
   static_assert(kBSlabs <= 16, "barrier block");
 };
@@ -44,8 +48,16 @@ __device__ __forceinline__ int scatter_prefix(int nt, int sft) {                
   return sft == 0 ? 0 : (sft == 1 ? nt : (sft == 2 ? nt + nt / 2 : 2 * nt));
 }
 
-template <int NT, int HE>      // HE > 0: box entries per chunk-plane of the wrapped-halo tiles (144 or 140); HE < 0: dense-box tiles of
-                               // exactly -HE rows (121 = the 11 x 11 box of the 33^2 / 65^2 grids); 0: dense-box tiles of any shape
+// Linear tiles (LIN; the 33^2 and 65^2 grids, where no wrapped-halo box shape fits the grid without a third more tiles): the
+// parity grid of one sample, padded by a halo row above and a halo column on the left (pitch P = W + 1 entries), is cut into
+// runs of 128 CONSECUTIVE entries.  Tile t covers entries P + 1 + 128 t ..; shift (a, b) of row r is entry - (a P + b), so one
+// box of P x R entries (R = 6 / 4 rows for P = 34 / 66) per channel block holds all four shifted operands at constant
+// offsets, exactly like the wrapped-halo box with bw = P plus a per-tile start offset.  Against the four dense boxes per
+// channel block this loads 26 / 34 KB instead of 62 KB and — what the layer was bound by — leaves room for a ring of 3 / 2
+// channel blocks in flight where the four dense slots were refilled inside the channel block that consumed them.
+template <int NT, int HE, bool LIN = false>
+                               // HE > 0: box entries per chunk-plane of the wrapped-halo tiles (144 or 140) or linear tiles (204, 264);
+                               // HE < 0: dense-box tiles of exactly -HE rows; 0: dense-box tiles of any shape
 __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap tmap_out,
                                                                 const ConvKernelParams p) {
@@ -53,6 +65,9 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
   constexpr bool HALO = HE > 0;
   constexpr int kHE = HE > 0 ? HE : (HE < 0 ? -HE : 144);      // entries per chunk-plane when they are a compile-time constant
   constexpr bool kFixed = HE != 0;
+  constexpr int kHStages = LIN ? Cfg::kARegion / (8 * kHE * 16) : Cfg::kHaloStages;          // 3 (204 entries), 2 (264)
+  constexpr int kHStageBytes = LIN ? 8 * kHE * 16 : Cfg::kHaloStageBytes;
+  static_assert(kHStages >= 2 && kHStages <= Cfg::kAStages, "A ring");
   constexpr int AS = Cfg::kAStages, BSL = Cfg::kBSlabs;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
@@ -63,7 +78,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* a_base = smem + 1024;
-  uint8_t* b_base = a_base + AS * kABytes;
+  uint8_t* b_base = smem + Cfg::kBOff;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,11 +135,14 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const uint32_t grp = g % Cfg::kGroups;
           const uint32_t a_par = (g & 1) ^ 1, b_par = ((g / Cfg::kGroups) & 1) ^ 1;
           uint8_t* bdst = b_base + grp * Cfg::kGroupBytes;
-          if (HALO && !((p.debug & 16) && g >= Cfg::kHaloStages)) {   // one box per channel block: tile + top row / left column halo
-            const uint32_t hs = g % Cfg::kHaloStages;
-            mbar_wait(&a_empty[hs], ((g / Cfg::kHaloStages) & 1) ^ 1);
+          if (HALO && !((p.debug & 16) && g >= kHStages)) {   // one box per channel block: tile + top row / left column halo
+            const uint32_t hs = g % kHStages;
+            mbar_wait(&a_empty[hs], ((g / kHStages) & 1) ^ 1);
             mbar_expect_tx(&a_full[hs], halo_bytes);
-            tma_load_5d(a_base + hs * Cfg::kHaloStageBytes, &tmap, &a_full[hs], (hx0 - 1) * 8, hy0 - 1, b0, kc * 4, 0);
+            if (LIN)      // 8-byte elements (two per entry): rows (128 ty) / P - 1 .. of the sample, from the halo column on
+              tma_load_5d(a_base + hs * kHStageBytes, &tmap, &a_full[hs], -2, (ty * kTileM) / p.bw - 1, b0, kc * 4, 0);
+            else
+              tma_load_5d(a_base + hs * kHStageBytes, &tmap, &a_full[hs], (hx0 - 1) * 8, hy0 - 1, b0, kc * 4, 0);
           }
 #pragma unroll
           for (int sft = 0; sft < 4; ++sft) {
@@ -171,14 +189,19 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * NT;
+        uint64_t lin_off = 0;            // linear tiles: first entry of the tile inside its box
+        if (LIN) {
+          const int t0 = ((tile % p.m_tiles) % p.tiles_y) * kTileM;
+          lin_off = static_cast<uint64_t>(t0 - (t0 / p.bw) * p.bw);
+        }
         for (int kc = 0; kc < p.kchunks; ++kc, ++g) {
           const uint32_t a_par = g & 1;
           const uint64_t grp_off = static_cast<uint64_t>(grp) * (Cfg::kGroupBytes >> 4);
           const bool b_skip = (p.debug & 4) && g >= Cfg::kGroups;
           const uint32_t acc0 = kc != 0 ? 1u : 0u;
           if (kFixed && !p.single) {
-            if (HALO && !((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
-            const uint64_t a_st = a_ring + static_cast<uint64_t>(hs) * (Cfg::kHaloStageBytes >> 4);
+            if (HALO && !((p.debug & 16) && g >= kHStages)) mbar_wait(&a_full[hs], hphase);
+            const uint64_t a_st = a_ring + static_cast<uint64_t>(hs) * (kHStageBytes >> 4) + lin_off;
 #pragma unroll
             for (int sft = 0; sft < 4; ++sft) {
               constexpr uint32_t kCol[4] = {0, 0, NT / 4, NT / 4};          // [oe|ee|eo|oo]: shifts (1,0), (1,1) start at ee
@@ -205,10 +228,10 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
               const uint32_t n_s = scatter_rows(NT, sft);
               const uint32_t coloff = sft >= 2 ? NT / 4 : 0;
               if (!HALO) mbar_wait(&a_full[sft], a_par);
-              else if (sft == 0 && !((p.debug & 16) && g >= Cfg::kHaloStages)) mbar_wait(&a_full[hs], hphase);
+              else if (sft == 0 && !((p.debug & 16) && g >= kHStages)) mbar_wait(&a_full[hs], hphase);
               if (!b_skip) mbar_wait(&b_full[grp * 4 + sft], gphase);
               tc_fence_after();
-              const uint64_t a_hi0 = HALO ? a_ring + static_cast<uint64_t>(hs) * (Cfg::kHaloStageBytes >> 4) + h_off[sft]
+              const uint64_t a_hi0 = HALO ? a_ring + static_cast<uint64_t>(hs) * (kHStageBytes >> 4) + lin_off + h_off[sft]
                                             : a_ring + ((sft * kABytes) >> 4);
               const uint64_t b_hi0 = b_ring[sft] + grp_off;
 #pragma unroll
@@ -228,7 +251,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
               umma_commit(&b_empty[grp * 4 + sft]);
             }
           }
-          if (HALO && ++hs == Cfg::kHaloStages) {
+          if (HALO && ++hs == kHStages) {
             hs = 0;
             hphase ^= 1;
           }
@@ -269,8 +292,15 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
       const int tb = m / p.tiles_y;
-      const int b = tb * p.bb + bl, y = ty * sy + yy, x = tx * sx + xx;
-      const bool valid = slot >= 0 && b < p.B && y < p.H && x < p.W;
+      int b = tb * p.bb + bl, y = ty * sy + yy, x = tx * sx + xx;
+      bool valid = slot >= 0 && b < p.B && y < p.H && x < p.W;
+      if (LIN) {                                          // entry P + 1 + 128 ty + r of the padded grid (tiles_x == 1)
+        const int e = p.bw + 1 + ty * kTileM + r;
+        y = e / p.bw - 1;
+        x = e - (y + 1) * p.bw - 1;
+        b = tb;
+        valid = x >= 0 && y < p.H;
+      }
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
@@ -356,6 +386,10 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
       e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, -121>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 204, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upconv_scatter_kernel<NT, 264, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("upconv_scatter: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
       return 1;
@@ -367,11 +401,18 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
   static const bool tma_off = [] { const char* e = getenv("SGR_TMA_STORE"); return e && e[0] == '0'; }();
   ConvKernelParams q = p;
   CUtensorMap tmap_out = tmap;
-  q.tma_store = (!tma_off && p.bb == 1 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;
+  q.tma_store = (!tma_off && p.bb == 1 && p.halo != 2 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;   // linear tiles are no boxes
   if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
   const int he = p.halo ? p.bw * p.box_rows : 0;
   cudaError_t le = cudaSuccess;
-  if (he == 144)
+  if (p.halo == 2 && he == 204)
+    le = launch_pdl(upconv_scatter_kernel<NT, 204, true>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
+  else if (p.halo == 2 && he == 264)
+    le = launch_pdl(upconv_scatter_kernel<NT, 264, true>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
+  else if (p.halo == 2) {
+    set_error("upconv_scatter: unsupported linear box of %d entries", he);
+    return 1;
+  } else if (he == 144)
     le = launch_pdl(upconv_scatter_kernel<NT, 144>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);
   else if (he == 140)
     le = launch_pdl(upconv_scatter_kernel<NT, 140>, dim3(std::min(total, sms)), dim3(256), Cfg::kSmemBytes, stream, tmap, tmap_out, q);

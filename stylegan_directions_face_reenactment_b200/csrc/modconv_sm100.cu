@@ -291,23 +291,26 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb, int planes, int chunk_box) {
+                        int bb, int planes, int chunk_box, bool wide) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return 1;
   }
   const cuuint64_t chunk_bytes = static_cast<cuuint64_t>(h) * w * 16;
-  const cuuint64_t dims[5] = {static_cast<cuuint64_t>(w) * 8, static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch),
+  // `wide`: the same memory as 8-byte elements (two per 8-channel entry), for boxes of more than 32 entries per row (a box
+  // dimension is limited to 256 elements); coordinates along x are then in half entries
+  const int epe = wide ? 2 : 8;      // elements per entry
+  const cuuint64_t dims[5] = {static_cast<cuuint64_t>(w) * epe, static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch),
                               static_cast<cuuint64_t>(channels / 8), 2};
   const cuuint64_t strides[4] = {static_cast<cuuint64_t>(w) * 16, chunk_bytes * (channels / 8), chunk_bytes,
                                  chunk_bytes * (channels / 8) * batch};
-  const cuuint32_t box[5] = {static_cast<cuuint32_t>(bw * 8), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bb),
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(bw * epe), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bb),
                              static_cast<cuuint32_t>(chunk_box), static_cast<cuuint32_t>(planes)};   // planes == 1: the hi plane only
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, wide ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for B=%d C=%d H=%d W=%d box=%dx%dx%d", static_cast<int>(r), batch,
               channels, h, w, bw, bh, bb);
@@ -500,6 +503,18 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
         p->bb = 1;
       }
     }
+    // Linear tiles (modconv_scatter_sm100.cu) where the wrapped-halo box lost: runs of 128 consecutive entries of the grid
+    // padded to pitch P = W + 1, one P x R box per channel block.  Instantiated for the 33^2 and 65^2 grids (204 / 264 entries).
+    static const bool lin_off = [] { const char* e = getenv("SGR_UP_LINEAR"); return e && e[0] == '0'; }();
+    if (!lin_off && !halo_off && !p->halo && p->bb == 1 && !a->single_pass && !getenv("SGR_UP_BOX")) {
+      const int P = p->W + 1, R = (2 * P - 1 + kTileM) / P + 1;
+      if (P * R == 204 || P * R == 264) {
+        p->halo = 2;
+        p->bw = P;
+        p->bh = 1;                      // unused: the tiles are runs of entries, not boxes
+        p->box_rows = R;
+      }
+    }
   } else {
     p->halo = 0;
     p->box_rows = 0;
@@ -514,6 +529,11 @@ int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt) {
     p->tiles_x = (p->W + p->bw - 2) / (p->bw - 1);
   }
   p->tiles_y = (p->H + p->bh - 1) / p->bh;
+  if (p->halo == 2) {             // entries P + 1 .. (H + 1) P - 1 of the padded grid in runs of 128
+    p->rows = kTileM;
+    p->tiles_x = 1;
+    p->tiles_y = (p->H * p->bw - 1 + kTileM - 1) / kTileM;
+  }
   p->tiles_b = (a->batch + p->bb - 1) / p->bb;
   p->m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
   const int n_total = a->cout * ((a->up == 1 || a->up == 2) ? 4 : 1);

@@ -316,7 +316,7 @@ static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* 
                             p.single ? 1 : 2))
       return 1;
   } else if (make_act_tensor_map(&tmap, args->x_c8, args->batch, args->cin, args->h_in, args->w_in, p.bw, p.halo ? p.box_rows : p.bh,
-                                 p.bb, p.single ? 1 : 2)) {
+                                 p.bb, p.single ? 1 : 2, kBlockK / 8, p.halo == 2)) {
     return 1;
   }
   if (args->up != 2)

@@ -122,7 +122,7 @@ struct FusedFirParams {
 int launch_modconv(const ConvKernelParams& p, const CUtensorMap& tmap, int nt, cudaStream_t stream);
 // host: build the 5-D tensor map over C8 activation planes
 int make_act_tensor_map(CUtensorMap* map, const void* base, int batch, int channels, int h, int w, int bw, int bh,
-                        int bb, int planes = 2, int chunk_box = kBlockK / 8);
+                        int bb, int planes = 2, int chunk_box = kBlockK / 8, bool wide = false);
 int conv_fill_params(const sgr_conv_args* a, ConvKernelParams* p, int* nt);
 // 5-D map over fp32 parity planes [B][4][C/4][Hp][Wp][4]: box = (cols x 4 floats, rows, groups of 4 channels, planes, 1 sample);
 // the defaults are the window the fused FIR producers load, the scatter GEMM stores (cols x rows, 8 groups, 1 plane) boxes
