@@ -340,19 +340,32 @@ struct DsJobs {
   DsJob job[SGR_MAX_STYLED];
   int n;
 };
-__global__ void ds_finish_kernel(const DsJobs jobs) {
+// 128 outputs per block, the reduction index cut into kRedSplit parts (one per group of 128 threads): a single 512-step
+// dependent chain per thread made these two kernels 70-80 us of pure latency.
+constexpr int kRedSplit = 4;
+__global__ void __launch_bounds__(128 * kRedSplit) ds_finish_kernel(const DsJobs jobs) {
   const DsJob& j = jobs.job[blockIdx.z];
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int part = threadIdx.x >> 7, t = threadIdx.x & 127;
+  const int i = blockIdx.x * 128 + t;
   __shared__ float qd[512];
+  __shared__ float red[kRedSplit][128];
   for (int o = threadIdx.x; o < j.cout; o += blockDim.x) {
     const float d = j.d[static_cast<size_t>(b) * j.cout + o];
     qd[o] = j.q[static_cast<size_t>(b) * j.cout + o] * d * d;
   }
   __syncthreads();
-  if (i >= j.cin) return;
   float acc = 0.f;
-  for (int o = 0; o < j.cout; ++o) acc = fmaf(qd[o], __ldg(j.wsq + static_cast<size_t>(o) * j.cin + i), acc);
+  if (i < j.cin) {
+    const int o0 = part * j.cout / kRedSplit, o1 = (part + 1) * j.cout / kRedSplit;
+#pragma unroll 8
+    for (int o = o0; o < o1; ++o) acc = fmaf(qd[o], __ldg(j.wsq + static_cast<size_t>(o) * j.cin + i), acc);
+  }
+  red[part][t] = acc;
+  __syncthreads();
+  if (part != 0 || i >= j.cin) return;
+#pragma unroll
+  for (int q = 1; q < kRedSplit; ++q) acc += red[q][t];
   const size_t k = static_cast<size_t>(b) * j.cin + i;
   j.ds[k] = j.ds[k] - j.s[k] * acc;
 }
@@ -367,15 +380,24 @@ struct LatJobs {
   LatJob job[SGR_MAX_STYLED + SGR_MAX_RGB];
   int n;
 };
-__global__ void dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, int latent_stride) {
+__global__ void __launch_bounds__(128 * kRedSplit) dlatent_kernel(const LatJobs jobs, float* __restrict__ dlatent, int latent_stride) {
   const LatJob& j = jobs.job[blockIdx.z];
   const int b = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;       // 0..511
+  const int part = threadIdx.x >> 7, t = threadIdx.x & 127;
+  const int k = blockIdx.x * 128 + t;                        // 0..511
   __shared__ float dsv[512];
+  __shared__ float red[kRedSplit][128];
   for (int i = threadIdx.x; i < j.cin; i += blockDim.x) dsv[i] = j.ds[static_cast<size_t>(b) * j.cin + i];
   __syncthreads();
   float acc = 0.f;
-  for (int i = 0; i < j.cin; ++i) acc = fmaf(dsv[i], __ldg(j.wm + static_cast<size_t>(i) * SGR_STYLE_DIM + k), acc);
+  const int i0 = part * j.cin / kRedSplit, i1 = (part + 1) * j.cin / kRedSplit;
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) acc = fmaf(dsv[i], __ldg(j.wm + static_cast<size_t>(i) * SGR_STYLE_DIM + k), acc);
+  red[part][t] = acc;
+  __syncthreads();
+  if (part != 0) return;
+#pragma unroll
+  for (int q = 1; q < kRedSplit; ++q) acc += red[q][t];
   atomicAdd(dlatent + static_cast<size_t>(b) * latent_stride + static_cast<size_t>(j.row) * SGR_STYLE_DIM + k,
             acc * 0.044194173824159216f);
 }
@@ -796,7 +818,7 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
       return 1;
     }
   }
-  ds_finish_kernel<<<dim3((cin_max + 127) / 128, batch, L), 128, 0, st>>>(dj);
+  ds_finish_kernel<<<dim3((cin_max + 127) / 128, batch, L), 128 * kRedSplit, 0, st>>>(dj);
   count_launch();
   if (!check_launch("ds_finish_kernel")) return 1;
   if (extras) {
@@ -839,7 +861,7 @@ int sgr_synthesis_backward_ex(const sgr_synthesis* net, const float* latent, int
     lj.job[lj.n++] = LatJob{F(pl.ds_off[l]), net->styled[l].mod_weight, net->styled[l].cin, net->styled[l].latent_row};
   for (int r = 0; r < R; ++r)
     lj.job[lj.n++] = LatJob{F(pl.dsrgb_off[r]), net->rgb[r].mod_weight, net->rgb[r].cin, net->rgb[r].latent_row};
-  dlatent_kernel<<<dim3(SGR_STYLE_DIM / 128, batch, lj.n), 128, 0, st>>>(lj, dlatent, latent_stride);
+  dlatent_kernel<<<dim3(SGR_STYLE_DIM / 128, batch, lj.n), 128 * kRedSplit, 0, st>>>(lj, dlatent, latent_stride);
   count_launch();
   return check_launch("dlatent_kernel") ? 0 : 1;
 }

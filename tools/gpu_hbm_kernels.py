@@ -2,9 +2,9 @@
 """Drives the HBM-bound kernels north_star names, at the bench shapes, for an `ncu --set full` capture:
 upfirdn2d_kernel in the generator's three modes (blur after an up-conv: pad (1,1) on the (2H+1)^2 grid; RGB-skip 2x
 upsampling: up 2, pad (2,1); its gradient: down 2, pad (1,1)), then one train()-mode forward + backward at 256^2/cm1
-(torgb_tail_kernel, bwd_act_kernel, up_bwd_prepare_kernel, param_sums_kernel, ...).
+(torgb_tail_kernel, bwd_act_kernel, up_bwd_prepare_kernel, ...).
 
-    ncu --set full --clock-control none -k regex:"upfirdn2d_kernel|torgb_tail|bwd_act|up_bwd_prepare|param_sums|frames_to_uint8" \
+    ncu --set full --clock-control none -k regex:"upfirdn2d_kernel|torgb_tail|bwd_act|up_bwd_prepare|frames_to_uint8" \
         -o gpurun_out/prof_hbm python tools/gpu_hbm_kernels.py
     python tools/ncu_summary.py hbm gpurun_out/prof_hbm.ncu-rep profiles/r2_hbm_kernels_ncu.md
 """

@@ -115,7 +115,7 @@ def hbm(src, dst_md, peak_gbs=None):
     with open(dst_md, 'w') as f:
         f.write('# `ncu --set full` of the HBM-bound kernels (tools/gpu_hbm_kernels.py)\n\n')
         f.write('Command: `ncu --set full --clock-control none -k regex:"upfirdn2d_kernel|torgb_tail|bwd_act|up_bwd_prepare|'
-                'param_sums|frames_to_uint8" -o gpurun_out/prof_hbm python tools/gpu_hbm_kernels.py`; table = `ncu -i ... --page raw '
+                'frames_to_uint8" -o gpurun_out/prof_hbm python tools/gpu_hbm_kernels.py`; table = `ncu -i ... --page raw '
                 '--csv` through tools/ncu_summary.py hbm.  GB/s = (dram read + write bytes) / duration; peak = %.0f GB/s '
                 '(MEASURED_PEAKS.json copy bandwidth).  Durations under ncu are cold-cache.\n\n' % peak_gbs)
         f.write('| kernel | grid | us | DRAM rd MB | DRAM wr MB | GB/s | of peak | DRAM % (ncu) | SM % | sectors/req ld | sectors/req st | regs |\n')
