@@ -110,8 +110,10 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
   pdl_launch_dependents();
   pdl_wait();
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int k_iters = 4 * p.kchunks;                  // k = kc * 4 + shift
+  // work item = (output tile, K slice): with fewer tiles than SMs (small batches, the 5^2 .. 33^2 grids) the channel blocks
+  // of a tile are cut into p.ksplit slices run by different CTAs; slice ks writes its raw planes to copy ks of the plane
+  // tensor ([ksplit][B][4][cout/4][H][W][4]) and up_finish_kernel adds the copies in slice order (deterministic)
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
       const uint32_t halo_bytes = static_cast<uint32_t>(kHE) * (p.single ? 64u : 128u);      // box = bw x box_rows entries
       const uint32_t b_row = p.single ? 64u : 128u;                                       // slabs are plane-major: hi half first
       uint32_t g = 0;                                  // running channel-block counter: ring slots and phases
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int ks = item % p.ksplit, tile = item / p.ksplit;
+        const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         const int n_tile = tile / p.m_tiles;
         int m = tile - n_tile * p.m_tiles;
         const int tx = m % p.tiles_x;
@@ -130,8 +134,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
         const int hx0 = tx * (p.bw - 1), hy0 = ty * p.bh;                  // wrapped-halo tiles: bw - 1 valid columns
         const uint8_t* wkc = reinterpret_cast<const uint8_t*>(p.wpacked) +
-                             static_cast<size_t>(n_tile) * p.kchunks * Cfg::kGroupBytes;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++g, wkc += Cfg::kGroupBytes) {
+                             (static_cast<size_t>(n_tile) * p.kchunks + kb0) * Cfg::kGroupBytes;
+        for (int kc = kb0; kc < kb1; ++kc, ++g, wkc += Cfg::kGroupBytes) {
           const uint32_t grp = g % Cfg::kGroups;
           const uint32_t a_par = (g & 1) ^ 1, b_par = ((g / Cfg::kGroups) & 1) ^ 1;
           uint8_t* bdst = b_base + grp * Cfg::kGroupBytes;
@@ -184,7 +188,9 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
       }
       uint32_t g = 0, tcount = 0;
       uint32_t hs = 0, hphase = 0, grp = 0, gphase = 0;      // ring slot + phase of the next halo stage / weight group
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tcount) {
+        const int ks = item % p.ksplit, tile = item / p.ksplit;
+        const int kb0 = ks * p.kchunks / p.ksplit, kb1 = (ks + 1) * p.kchunks / p.ksplit;
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
@@ -194,11 +200,11 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const int t0 = ((tile % p.m_tiles) % p.tiles_y) * kTileM;
           lin_off = static_cast<uint64_t>(t0 - (t0 / p.bw) * p.bw);
         }
-        for (int kc = 0; kc < p.kchunks; ++kc, ++g) {
+        for (int kc = kb0; kc < kb1; ++kc, ++g) {
           const uint32_t a_par = g & 1;
           const uint64_t grp_off = static_cast<uint64_t>(grp) * (Cfg::kGroupBytes >> 4);
           const bool b_skip = (p.debug & 4) && g >= Cfg::kGroups;
-          const uint32_t acc0 = kc != 0 ? 1u : 0u;
+          const uint32_t acc0 = kc != kb0 ? 1u : 0u;
           if (kFixed && !p.single) {
             if (HALO && !((p.debug & 16) && g >= kHStages)) mbar_wait(&a_full[hs], hphase);
             const uint64_t a_st = a_ring + static_cast<uint64_t>(hs) * (kHStageBytes >> 4) + lin_off;
@@ -285,7 +291,8 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
     constexpr int CT = NT / 4;
     const size_t group_stride = static_cast<size_t>(p.H) * p.W * 4;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tcount) {
+      const int ks = item % p.ksplit, tile = item / p.ksplit;
       const int n_tile = tile / p.m_tiles;
       int m = tile - n_tile * p.m_tiles;
       const int tx = m % p.tiles_x;
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
             const int g0 = (n_tile * CT + (c % CT)) >> 2;
             asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                          ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(smem_u32(stg)), "r"(tx * sx * 4), "r"(ty * sy), "r"(g0),
-                         "r"(plane), "r"(tb)
+                         "r"(plane), "r"(ks * p.B + tb)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) upconv_scatter_kernel(const __grid_con
           const int c = ci * 32;
           const int plane = c / CT;
           const int o0 = n_tile * CT + (c % CT);
-          float* tptr = p.t_out + ((static_cast<size_t>(b) * 4 + plane) * (p.cout >> 2) + (o0 >> 2)) * group_stride +
+          float* tptr = p.t_out + ((static_cast<size_t>(ks * p.B + b) * 4 + plane) * (p.cout >> 2) + (o0 >> 2)) * group_stride +
                         (static_cast<size_t>(y) * p.W + x) * 4;
           const float* vv = v[ci & 1];
 #pragma unroll
@@ -396,13 +403,13 @@ static int launch_scatter_nt(const ConvKernelParams& p, const CUtensorMap& tmap,
     }
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   // TMA-store epilogue: one sample per tile (the layers of 16x16 and larger), whole 32-column chunks of one plane
   static const bool tma_off = [] { const char* e = getenv("SGR_TMA_STORE"); return e && e[0] == '0'; }();
   ConvKernelParams q = p;
   CUtensorMap tmap_out = tmap;
   q.tma_store = (!tma_off && p.bb == 1 && p.halo != 2 && NT / 4 >= 32 && !(p.debug & 3)) ? 1 : 0;   // linear tiles are no boxes
-  if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
+  if (q.tma_store && make_plane_tensor_map(&tmap_out, p.t_out, p.B * p.ksplit, p.cout, p.H, p.W, p.halo ? p.bw - 1 : p.bw, p.bh, 8, 1)) return 1;
   const int he = p.halo ? p.bw * p.box_rows : 0;
   cudaError_t le = cudaSuccess;
   if (p.halo == 2 && he == 204)

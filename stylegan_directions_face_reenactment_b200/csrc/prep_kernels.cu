@@ -213,16 +213,19 @@ __global__ void style_kernel(const StyleJobs jobs, const float* __restrict__ lat
 // (One warp per (b, o) re-read each wsq row once per sample: 270 MB of L2 traffic at B = 32.)
 constexpr int kTableOutPerBlock = 16;
 constexpr int kTableMaxCinPerLane = 16;          // cin <= 512
+// NB = samples per block: 32, or 4 for the small-batch calls (batch <= 4: a block of 32 mostly-empty sample slots made the
+// first launch of a batch-1 frame 16 us long)
+template <int NB>
 __global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int batch) {
-  extern __shared__ float s2[];                        // [32][cin]
+  extern __shared__ float s2[];                        // [NB][cin]
   const TableJob& j = jobs.job[blockIdx.y];
   const int o0 = blockIdx.x * kTableOutPerBlock;
   if (o0 >= j.cout) return;
-  const int b0 = blockIdx.z * 32;
-  const int nb = min(32, batch - b0);
+  const int b0 = blockIdx.z * NB;
+  const int nb = min(NB, batch - b0);
   for (int i = threadIdx.x; i < j.cin; i += blockDim.x) {           // no integer division: column i, all samples
-#pragma unroll 8
-    for (int b = 0; b < 32; ++b) {
+#pragma unroll (NB < 8 ? NB : 8)
+    for (int b = 0; b < NB; ++b) {
       const float v = b < nb ? __ldg(j.s + static_cast<size_t>(b0 + b) * j.cin + i) : 0.f;
       s2[b * j.cin + i] = v * v;
     }
@@ -238,16 +241,16 @@ __global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int ba
     const bool has_b = ob < j.cout;
     const float* qa = j.wsq + static_cast<size_t>(oa) * j.cin;
     const float* qb = j.wsq + static_cast<size_t>(has_b ? ob : oa) * j.cin;
-    float acc[32], bcc[32];
+    float acc[NB], bcc[NB];
 #pragma unroll
-    for (int b = 0; b < 32; ++b) acc[b] = bcc[b] = 0.f;
+    for (int b = 0; b < NB; ++b) acc[b] = bcc[b] = 0.f;
 #pragma unroll
     for (int t = 0; t < kTableMaxCinPerLane; ++t) {
       if (32 * t < j.cin) {                          // warp-uniform
         const float wa = __ldg(qa + lane + 32 * t), wb = __ldg(qb + lane + 32 * t);
         const float* col = s2 + lane + 32 * t;
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
+        for (int b = 0; b < NB; ++b) {
           const float sv = col[b * j.cin];
           acc[b] = fmaf(sv, wa, acc[b]);
           bcc[b] = fmaf(sv, wb, bcc[b]);
@@ -256,15 +259,30 @@ __global__ void __launch_bounds__(256) table_kernel(const TableJobs jobs, int ba
     }
     // reduce-scatter over the lanes: after the step with offset `off` a lane keeps the half of the samples whose bit
     // `off` equals its own, so lane b ends with the total of sample b in acc[0] / bcc[0]
+    if constexpr (NB == 32) {
 #pragma unroll
-    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-      const bool up = (lane & off) != 0;
+      for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
 #pragma unroll
-      for (int k = 0; k < n / 2; ++k) {
-        const float send = up ? acc[k] : acc[k + n / 2], keep = up ? acc[k + n / 2] : acc[k];
-        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        const float send2 = up ? bcc[k] : bcc[k + n / 2], keep2 = up ? bcc[k + n / 2] : bcc[k];
-        bcc[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+        for (int k = 0; k < n / 2; ++k) {
+          const float send = up ? acc[k] : acc[k + n / 2], keep = up ? acc[k + n / 2] : acc[k];
+          acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          const float send2 = up ? bcc[k] : bcc[k + n / 2], keep2 = up ? bcc[k + n / 2] : bcc[k];
+          bcc[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+        }
+      }
+    } else {                                           // few samples: plain butterfly per sample, lane b keeps sample b
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+          bcc[k] += __shfl_xor_sync(0xffffffffu, bcc[k], off);
+        }
+#pragma unroll
+      for (int k = 1; k < NB; ++k) {
+        acc[0] = lane == k ? acc[k] : acc[0];
+        bcc[0] = lane == k ? bcc[k] : bcc[0];
       }
     }
     if (lane < nb) {
@@ -422,17 +440,23 @@ int table_jobs_launch(const TableJobs& jobs, int batch, cudaStream_t st) {
       return 1;
     }
   }
+  if (batch <= 4) {                                    // [4][cin <= 512] floats: within the default shared-memory limit
+    dim3 grid4((cmax + kTableOutPerBlock - 1) / kTableOutPerBlock, jobs.n, 1);
+    table_kernel<4><<<grid4, 256, 4 * cin_max * 4, st>>>(jobs, batch);
+    count_launch();
+    return check_launch("table_kernel") ? 0 : 1;
+  }
   const int smem = 32 * cin_max * 4;
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    if (cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(table_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("table_kernel: cin %d needs %d bytes of shared memory", cin_max, smem);
       return 1;
     }
     configured_smem = smem;
   }
   dim3 grid((cmax + kTableOutPerBlock - 1) / kTableOutPerBlock, jobs.n, (batch + 31) / 32);
-  table_kernel<<<grid, 256, smem, st>>>(jobs, batch);
+  table_kernel<32><<<grid, 256, smem, st>>>(jobs, batch);
   count_launch();
   return check_launch("table_kernel") ? 0 : 1;
 }

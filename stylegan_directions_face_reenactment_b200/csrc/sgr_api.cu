@@ -1,4 +1,6 @@
 // extern "C" surface of libsgr.so (include/sgr.h) and the whole-network orchestration.
+#include <algorithm>
+
 #include <stdarg.h>
 #include <stdlib.h>
 #include <stdio.h>
@@ -18,15 +20,22 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { ++g_launches; }
-// Programmatic dependent launch of the forward chain (sgr_internal.h launch_pdl, sgr_ptx.cuh pdl_wait): OFF by default.
-// Measured on one B200 (B = 32, 256^2, tools/gpu/call25.sh, same box): 3.04 ms per step without, 3.17 ms with it (sustained
-// 3.27 vs 3.43 ms) — the persistent GEMM CTAs hold a whole SM's shared memory and TMEM, so a dependent CTA can only become
-// resident when a primary CTA has already exited, and the early-resident CTAs then sit in griddepcontrol.wait holding that
-// SM; nothing of the ~3 us prologue is recovered.  SGR_PDL=1 enables it (results are identical either way).
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("SGR_PDL"); return e && e[0] == '1'; }();
-  return on;
-}
+// Programmatic dependent launch of the forward chain (sgr_internal.h launch_pdl, sgr_ptx.cuh pdl_wait).
+// Large batches: OFF.  Measured on one B200 (B = 32, 256^2, tools/gpu/call25.sh, same box): 3.04 ms per step without, 3.17 ms
+// with it (sustained 3.27 vs 3.43 ms) — the persistent GEMM CTAs hold a whole SM's shared memory and TMEM, so a dependent CTA
+// can only become resident when a primary CTA has already exited, and the early-resident CTAs then sit in
+// griddepcontrol.wait holding that SM; nothing of the ~3 us prologue is recovered.
+// Small batches (<= 4 frames per call, how run_inference.py drives the generator): ON.  Most grids there are smaller than
+// the machine, the dependents set themselves up (barrier init, TMEM allocation, descriptor prefetch) on idle SMs while the
+// predecessor drains: batch 1 0.429 -> 0.413 ms per frame, batch 2 0.519 -> 0.492 ms (captured graph, same box).
+// SGR_PDL=1 / 0 forces it on / off for every batch (results are identical either way).
+static const int g_pdl_mode = [] {
+  const char* e = getenv("SGR_PDL");
+  return !e ? 2 : (e[0] == '1' ? 1 : 0);
+}();
+static thread_local bool g_pdl_small_batch = false;
+bool pdl_enabled() { return g_pdl_mode == 1 || (g_pdl_mode == 2 && g_pdl_small_batch); }
+void pdl_small_batch(bool on) { g_pdl_small_batch = on; }
 bool check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -291,6 +300,29 @@ static void fill_fused_fir(const sgr_conv_args* up, FusedFirParams* f) {
   f->s2 = up->s2; f->act = up->act; f->act_gain = up->act_gain; f->out_scale = act_scale(up->out_format);
 }
 
+// Split-K of the scatter up-conv (modconv_scatter_sm100.cu): with fewer tiles than half the SMs (batch 1-4, the 5^2 .. 33^2
+// grids: 8 .. 36 CTAs walking all channel blocks one after the other, ~25 us each at batch 1) the channel blocks are cut into
+// up to 8 slices; every slice writes its own copy of the raw parity planes into the split-K scratch and the FIR pass
+// (up_finish_kernel) adds the copies on load, in slice order.  Not combined with the fused FIR producers, which read the
+// planes by TMA.  SGR_UP_SPLITK=0 disables it, any other number caps the slice count.
+static int scatter_ksplit(const sgr_conv_args* a, const ConvKernelParams& p) {
+  static const int cap = [] {
+    const char* e = getenv("SGR_UP_SPLITK");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);          // up_finish_kernel adds at most 8 copies
+  }();
+  if (cap < 2 || !a->splitk_scratch || p.debug) return 1;
+  const int sms = num_sms();
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (sms <= 0 || tiles <= 0 || 2 * tiles > sms) return 1;
+  int s = std::min(cap, sms / tiles);
+  s = std::min(s, p.kchunks / 2);                    // at least two 32-channel blocks per slice
+  const size_t plane_bytes = static_cast<size_t>(a->batch) * 4 * a->cout * (a->h_in + 1) * (a->w_in + 1) * 4;
+  while (s > 1 && s * plane_bytes > a->splitk_scratch_bytes) --s;
+  while (s & (s - 1)) --s;                           // 1, 2, 4 or 8 copies (up_finish_kernel instantiations)
+  return s < 2 ? 1 : s;
+}
+
 // defer_fir: (up == 2) run the scatter GEMM only; the consumer applies the FIR pass (fused_src = that layer's arguments)
 static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* fused_src, bool defer_fir, void* stream) {
   if (!have_device()) return 1;
@@ -319,18 +351,27 @@ static int modconv_forward_impl(const sgr_conv_args* args, const sgr_conv_args* 
                                  p.bb, p.single ? 1 : 2, kBlockK / 8, p.halo == 2)) {
     return 1;
   }
-  if (args->up != 2)
+  int up_slices = 1;
+  if (args->up != 2) {
     set_ksplit(&p, choose_ksplit(args, p.m_tiles * p.n_tiles, p.ntaps * p.kchunks, 8, static_cast<size_t>(kTileM) * nt * 4));
+  } else if (!defer_fir) {
+    up_slices = scatter_ksplit(args, p);
+    if (up_slices > 1) {                 // (p.acc_scale is not used by the scatter kernel: up_finish applies the plane scales)
+      p.ksplit = up_slices;
+      p.t_out = static_cast<float*>(args->splitk_scratch);
+    }
+  }
   const bool prof = prof_begin(static_cast<cudaStream_t>(stream));
   rc = args->up == 2 ? launch_upconv_scatter(p, tmap, nt, static_cast<cudaStream_t>(stream))
                      : launch_modconv(p, tmap, nt, static_cast<cudaStream_t>(stream));
-  if (rc == 0 && p.ksplit > 1) rc = splitk_finish_launch(p, static_cast<cudaStream_t>(stream));
+  if (rc == 0 && args->up != 2 && p.ksplit > 1) rc = splitk_finish_launch(p, static_cast<cudaStream_t>(stream));
   if (prof) prof_end(static_cast<cudaStream_t>(stream));
   if (rc == 0 && args->up == 2 && !defer_fir) {
     float base, comp;
     up_plane_scales(args, &base, &comp);
+    comp /= static_cast<float>(up_slices);           // each slice's accumulation chain is 1 / up_slices as long
     const bool prof2 = prof_begin(static_cast<cudaStream_t>(stream), 1);
-    rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream));
+    rc = up_finish_launch(args, base, comp, static_cast<cudaStream_t>(stream), up_slices > 1 ? p.t_out : nullptr, up_slices);
     if (prof2) prof_end(static_cast<cudaStream_t>(stream));
   }
   return rc;
@@ -385,6 +426,10 @@ int sgr_synthesis_forward_ex(const sgr_synthesis* net, const float* latent, int 
   if (!have_device()) return 1;
   SynthPlan pl;
   if (plan_synthesis(net, batch, &pl)) return 1;
+  struct PdlScope {                                    // programmatic dependent launch for small-batch calls (pdl_enabled())
+    explicit PdlScope(bool on) { pdl_small_batch(on); }
+    ~PdlScope() { pdl_small_batch(false); }
+  } pdl_scope(batch <= 4);
   unsigned char* frames_u8 = extras ? extras->frames_u8 : nullptr;
   if (frames_u8 && (extras->u8_h <= 0 || extras->u8_w <= 0 || net->size % extras->u8_h != 0 || net->size % extras->u8_w != 0)) {
     set_error("synthesis_forward: uint8 frame size %dx%d must divide the network size %d", extras->u8_h, extras->u8_w, net->size);

@@ -30,7 +30,8 @@ void tile_box(int h, int w, int* bw, int* bh, int* bb);
 void tile_box_search(int batch, int h, int w, int* bw, int* bh, int* bb);
 
 void set_error(const char* fmt, ...);
-bool pdl_enabled();          // SGR_PDL=0 disables programmatic dependent launch (sgr_api.cu)
+bool pdl_enabled();          // programmatic dependent launch: small-batch forward calls, or SGR_PDL=1 (sgr_api.cu)
+void pdl_small_batch(bool on);
 
 // Launch with programmatic stream serialization: the kernel may start while its predecessor drains (sgr_ptx.cuh pdl_wait()).
 // ONLY for kernels that call pdl_wait() before their first dependent global access.
@@ -199,7 +200,9 @@ int torgb_tail_u8_launch(const float* rgb_acc, int slots, const float* bias, con
                          unsigned char* out, int batch, int H, int W, int out_h, int out_w, cudaStream_t st);
 int frames_to_uint8_launch(const float* x, unsigned char* y, int batch, int H, int W, int out_h, int out_w, cudaStream_t st);
 // up_finish_sm100.cu: FIR + fused epilogue over the parity planes of a scatter up-conv
-int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st);
+// planes / nslices: the plane tensor when it is not a->t_scratch (split-K scatter GEMM: nslices copies, added on load)
+int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st, const float* planes = nullptr,
+                     int nslices = 1);
 bool acc_comp_enabled();
 
 }  // namespace sgr

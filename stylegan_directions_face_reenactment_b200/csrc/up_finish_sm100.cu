@@ -35,6 +35,8 @@ struct UpFinishParams {
   int single_out;              // single-pass consumers: the lo plane is not written
   int strips;                  // column strips of 14 output-producing columns
   int rows;                    // input rows walked by one warp
+  int nslices;                 // split-K scatter GEMM: `t` holds this many copies of the plane tensor (one per K slice), added
+  long long slice_stride;      // in slice order on load; floats between copies
 };
 
 // Work decomposition (instruction-issue bound otherwise: the generic 16-tap form costs ~37 instructions per output):
@@ -82,8 +84,8 @@ __device__ __forceinline__ void split_pair_bf16(float v0, float v1, uint32_t& hi
 }
 
 // ROWS: input rows walked by one warp (H % ROWS == 0, so the loop is uniform and the shuffles need no re-convergence code)
-template <int ROWS, int FMT, bool F32OUT>
-__global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams p) {
+template <int ROWS, int FMT, bool F32OUT, int NSL = 1>      // NSL: plane copies of a split-K scatter GEMM (1, 2, 4, 8)
+__global__ void __launch_bounds__(128, NSL > 1 ? 2 : 4) up_finish_kernel(const UpFinishParams p) {
   // sc[0..3] = gy (vertical taps, flipped), sc[4..7] = gx (horizontal taps, flipped, normalised by the tap sum)
   __shared__ float sc[8];
   pdl_launch_dependents();
@@ -154,19 +156,35 @@ __global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams 
   const float* nz_ptr = p.noise ? p.noise + static_cast<size_t>(b) * p.noise_bstride + static_cast<size_t>(2 * m0) * Wo + 2 * (out_ok ? n : 0)
                                 : nullptr;
 
+  // split-K scatter GEMM (NSL > 1; small batches / small grids): every plane element is the sum of NSL partial planes, added in
+  // slice order; all copies are requested before the first add, so a load costs one memory latency, not one per slice
+  auto ld = [&](const float* q, bool ok) -> F4 {
+    F4 r = f4_load(q, ok);
+    if (NSL > 1) {
+      F4 t[NSL > 1 ? NSL - 1 : 1];
+#pragma unroll
+      for (int sl = 1; sl < NSL; ++sl) t[sl - 1] = f4_load(q + sl * p.slice_stride, ok);
+#pragma unroll
+      for (int sl = 1; sl < NSL; ++sl) {
+        r.a = __fadd2_rn(r.a, t[sl - 1].a);
+        r.b = __fadd2_rn(r.b, t[sl - 1].b);
+      }
+    }
+    return r;
+  };
   // register window: odd planes at rows m-1, m; even planes at row m
-  F4 oe_m1 = f4_load(t_oe - row_stride, col_ok && m0 > 0);
-  F4 oo_m1 = f4_load(t_oo - row_stride, col_ok && m0 > 0);
-  F4 ee_0 = f4_load(t_ee, col_ok);
-  F4 eo_0 = f4_load(t_eo, col_ok);
-  F4 oe_0 = f4_load(t_oe, col_ok);
-  F4 oo_0 = f4_load(t_oo, col_ok);
+  F4 oe_m1 = ld(t_oe - row_stride, col_ok && m0 > 0);
+  F4 oo_m1 = ld(t_oo - row_stride, col_ok && m0 > 0);
+  F4 ee_0 = ld(t_ee, col_ok);
+  F4 eo_0 = ld(t_eo, col_ok);
+  F4 oe_0 = ld(t_oe, col_ok);
+  F4 oo_0 = ld(t_oo, col_ok);
 
   // software pipeline: the plane rows (and noise) of the NEXT iteration are requested before this iteration's math, so
   // the HBM latency overlaps ~400 instructions of work instead of stalling the first FMA (61 % long-scoreboard stalls
   // without it)
   t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;        // row m0+1 <= H always exists
-  F4 ee_n = f4_load(t_ee, col_ok), eo_n = f4_load(t_eo, col_ok), oe_n = f4_load(t_oe, col_ok), oo_n = f4_load(t_oo, col_ok);
+  F4 ee_n = ld(t_ee, col_ok), eo_n = ld(t_eo, col_ok), oe_n = ld(t_oe, col_ok), oo_n = ld(t_oo, col_ok);
   float2 nz_n[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   if (nz_ptr) {
     nz_n[0] = __ldg(reinterpret_cast<const float2*>(nz_ptr));
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams 
     const float2 nz_c[2] = {nz_n[0], nz_n[1]};
     if (i + 1 < ROWS) {
       t_oe += row_stride; t_ee += row_stride; t_eo += row_stride; t_oo += row_stride;    // row m+2 <= H inside the strip
-      ee_n = f4_load(t_ee, col_ok); eo_n = f4_load(t_eo, col_ok); oe_n = f4_load(t_oe, col_ok); oo_n = f4_load(t_oo, col_ok);
+      ee_n = ld(t_ee, col_ok); eo_n = ld(t_eo, col_ok); oe_n = ld(t_oe, col_ok); oo_n = ld(t_oo, col_ok);
       if (nz_ptr) {
         nz_ptr += 2 * Wo;
         nz_n[0] = __ldg(reinterpret_cast<const float2*>(nz_ptr));
@@ -261,22 +279,39 @@ __global__ void __launch_bounds__(128, 4) up_finish_kernel(const UpFinishParams 
   }
 }
 
-template <int ROWS>
-static void up_finish_dispatch(const UpFinishParams& p, dim3 grid, int threads, cudaStream_t st) {
+template <int ROWS, int NSL>
+static void up_finish_dispatch_nsl(const UpFinishParams& p, dim3 grid, int threads, cudaStream_t st) {
   const bool f32 = p.out_f32 != nullptr;
   if (p.out_fmt == kFmtBF16) {
-    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtBF16, true>, grid, dim3(threads), 0, st, p);
-    else launch_pdl(up_finish_kernel<ROWS, kFmtBF16, false>, grid, dim3(threads), 0, st, p);
+    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtBF16, true, NSL>, grid, dim3(threads), 0, st, p);
+    else launch_pdl(up_finish_kernel<ROWS, kFmtBF16, false, NSL>, grid, dim3(threads), 0, st, p);
   } else {
-    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtFP16, true>, grid, dim3(threads), 0, st, p);
-    else launch_pdl(up_finish_kernel<ROWS, kFmtFP16, false>, grid, dim3(threads), 0, st, p);
+    if (f32) launch_pdl(up_finish_kernel<ROWS, kFmtFP16, true, NSL>, grid, dim3(threads), 0, st, p);
+    else launch_pdl(up_finish_kernel<ROWS, kFmtFP16, false, NSL>, grid, dim3(threads), 0, st, p);
   }
 }
 
-int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st) {
+template <int ROWS>
+static void up_finish_dispatch(const UpFinishParams& p, dim3 grid, int threads, cudaStream_t st) {
+  switch (p.nslices) {
+    case 8: up_finish_dispatch_nsl<ROWS, 8>(p, grid, threads, st); break;
+    case 4: up_finish_dispatch_nsl<ROWS, 4>(p, grid, threads, st); break;
+    case 2: up_finish_dispatch_nsl<ROWS, 2>(p, grid, threads, st); break;
+    default: up_finish_dispatch_nsl<ROWS, 1>(p, grid, threads, st); break;
+  }
+}
+
+int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap, cudaStream_t st, const float* planes,
+                     int nslices) {
   UpFinishParams p;
   p.B = a->batch; p.C = a->cout; p.H = a->h_in; p.W = a->w_in;
-  p.t = a->t_scratch;
+  p.t = planes ? planes : a->t_scratch;
+  if (nslices != 1 && nslices != 2 && nslices != 4 && nslices != 8) {
+    set_error("up_finish: %d plane copies (1, 2, 4 or 8)", nslices);
+    return 1;
+  }
+  p.nslices = nslices < 1 ? 1 : nslices;
+  p.slice_stride = static_cast<long long>(a->batch) * 4 * a->cout * (a->h_in + 1) * (a->w_in + 1);
   p.fir = a->fir;
   p.demod = a->demod;
   const int taps[4] = {2, 4, 2, 1};                  // MMAs chains accumulated per plane: oe, ee, eo, oo
@@ -297,6 +332,13 @@ int up_finish_launch(const sgr_conv_args* a, float acc_scale, float comp_per_tap
   // rows per warp: long strips amortise the two preloaded window rows, short ones keep small layers parallel
   int rows = a->h_in >= 64 ? 16 : (a->h_in >= 32 ? 8 : (a->h_in >= 8 ? 4 : 2));
   while (a->h_in % rows != 0) rows >>= 1;            // any height: fall back to shorter strips (1 always divides)
+  // small batches: a warp walks its rows one after the other (a chain of `rows` + 2 memory latencies), so when the whole
+  // launch has fewer warps than the machine wants (~8 per SM) shorter strips finish sooner (batch 1, 64 -> 128: 16 -> 8 us)
+  {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const long long per_row_group = static_cast<long long>(p.strips) * (a->cout / 8) * a->batch;
+    while (rows > 1 && per_row_group * (a->h_in / rows) < 8LL * sms) rows >>= 1;
+  }
   p.rows = rows;
   const int rgroups = a->h_in / rows;
   int warps = 4;

@@ -295,6 +295,47 @@ def test_fused_fir_producer_mode_matches_separate_pass(pkg, tmp_path):
     assert float(np.abs(fused - ref.numpy()).max()) <= 1e-3
 
 
+def test_small_batch_scatter_splitk_and_pdl_match_the_plain_path(pkg, tmp_path):
+    """Batch 1-4 calls (how run_inference.py drives the generator) cut the channel blocks of the scatter up-convs into K slices
+    whose partial parity planes the FIR pass adds on load (csrc/sgr_api.cu scatter_ksplit) and launch the chain with
+    programmatic dependent launch.  Against the same call with both switched off (SGR_UP_SPLITK=0 SGR_PDL=0; read once per
+    process, so that mode runs in a subprocess): same image to accumulate-rounding level, and within the 1e-3 bar of the oracle."""
+    import os
+    import subprocess
+    import sys
+    size, cm = 256, 1
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / 'plain.npz')
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from oracle import stylegan2_oracle as orc\n"
+            "import stylegan_directions_face_reenactment_b200 as pkg\n"
+            "sd = orc.seeded_state_dict(%d, %d, seed=6)\n"
+            "G = pkg.Generator(%d, 512, 8, channel_multiplier=%d); G.load_state_dict(sd, strict=True); G = G.cuda().eval()\n"
+            "res = {}\n"
+            "for b in (1, 3):\n"
+            "    w = orc.seeded_wplus(sd, b, G.n_latent, seed=9).cuda()\n"
+            "    with torch.no_grad(): res['b%%d' %% b] = G([w], input_is_latent=True)[0].cpu().numpy()\n"
+            "np.savez(%r, **res)\n") % (root, size, cm, size, cm, out)
+    env = dict(os.environ, SGR_UP_SPLITK='0', SGR_PDL='0')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, timeout=300)
+    plain = np.load(out)
+    sd = orc.seeded_state_dict(size, cm, seed=6)
+    G = pkg.Generator(size, 512, 8, channel_multiplier=cm)
+    G.load_state_dict(sd, strict=True)
+    G = G.cuda().eval()
+    for b in (1, 3):
+        wplus = orc.seeded_wplus(sd, b, G.n_latent, seed=9)
+        with torch.no_grad():
+            img = G([wplus.cuda()], input_is_latent=True)[0]
+            again = G([wplus.cuda()], input_is_latent=True)[0]
+        assert torch.equal(img, again)                        # slices are added in slice order: bit-identical repeats
+        assert err(img, plain['b%d' % b]) <= 2e-4
+        if b == 1:
+            with torch.no_grad():
+                ref, _ = orc.generator_forward(sd, [wplus], size, cm, input_is_latent=True)
+            assert err(img, ref.numpy()) <= 1e-3
+
+
 def test_weight_cache_invalidation(pkg):
     size, cm = 8, 2
     sd = orc.seeded_state_dict(size, cm, seed=8)

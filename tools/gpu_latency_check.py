@@ -14,7 +14,8 @@ G = pkg.Generator(256, 512, 8, channel_multiplier=1)
 G.load_state_dict(sd, strict=True)
 G = G.cuda().eval().requires_grad_(False)
 trunc = orc.seeded_wplus(sd, 1, 1, seed=7)[:, 0].cuda()
-for B in (1, 4, 32):
+BATCHES = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [1, 4, 32]
+for B in BATCHES:
     w = orc.seeded_wplus(sd, B, G.n_latent, seed=3).cuda()
     for graphs in (False, True):
         G.enable_cuda_graphs(graphs)
