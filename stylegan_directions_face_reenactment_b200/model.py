@@ -151,7 +151,7 @@ class ModulatedConv2d(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == '_pack_cache' else copy.deepcopy(v, memo)
+            new.__dict__[k] = {} if k in ('_pack_cache', '_fill_plans') else copy.deepcopy(v, memo)
         return new
 
     def up_mode(self):
@@ -191,8 +191,7 @@ class ModulatedConv2d(nn.Module):
             # (only the weight's version moved; a cache that has collected many layouts is dropped instead of refilled)
             if in_place:
                 cache['version'] = version
-                for slot, (packed, wsq) in [(k, v) for k, v in cache.items() if k != 'version']:
-                    self._fill_packed(slot, packed, wsq)
+                self._refill_in_place(cache)
             else:                                                # new storage / new FIR: every packed variant is stale
                 cache.clear()
                 cache['version'] = version
@@ -222,6 +221,25 @@ class ModulatedConv2d(nn.Module):
             cin += 32 - cin % 32
         return cout, cin
 
+    def _refill_in_place(self, cache):
+        """Refill every cached packed variant after an in-place weight update (one optimizer step of optimize_g).  The batch-1
+        fine-tuning step is bound by host time, so the argument tuple of each sgr_pack_modconv_weight call is recorded the first
+        time (`_fill_plans`: valid while the weight storage, the FIR buffer and the packed buffers stay where they are) and the
+        refill is then one ctypes call per variant, with one device guard and one stream lookup for all of them."""
+        plans = self.__dict__.setdefault('_fill_plans', {})
+        fir = self.blur.kernel if self.upsample else None
+        here = (self.weight.data_ptr(), None if fir is None else fir.data_ptr())
+        with torch.cuda.device(self.weight.device):
+            st = N.stream()
+            lib = N.lib()
+            for slot, (packed, wsq) in [(k, v) for k, v in cache.items() if k != 'version']:
+                plan = plans.get(slot)
+                if plan is not None and plan[0] == here and plan[1] == (packed.data_ptr(), None if wsq is None else wsq.data_ptr()):
+                    N.check(lib.sgr_pack_modconv_weight(*plan[2], st), 'sgr_pack_modconv_weight')
+                else:
+                    plans.pop(slot, None)
+                    self._fill_packed(slot, packed, wsq)
+
     def _fill_packed(self, slot, packed, wsq):
         transpose, fmt, nt, up_mode = slot
         cout, cin, ks = self.out_channel, self.in_channel, self.kernel_size
@@ -237,9 +255,15 @@ class ModulatedConv2d(nn.Module):
             wd = wd.contiguous().float()
         fir = self.blur.kernel if self.upsample else None
         firc = None if fir is None else fir.detach().contiguous().float()
+        args = (N.ptr(wd), N.ptr(firc), cout, cin, ks, up_mode, int(transpose), fmt, nt, N.ptr(packed), N.ptr(wsq))
         with torch.cuda.device(wd.device):
-            N.check(N.lib().sgr_pack_modconv_weight(N.ptr(wd), N.ptr(firc), cout, cin, ks, up_mode, int(transpose),
-                                                    fmt, nt, N.ptr(packed), N.ptr(wsq), N.stream()), 'sgr_pack_modconv_weight')
+            N.check(N.lib().sgr_pack_modconv_weight(*args, N.stream()), 'sgr_pack_modconv_weight')
+        # the operands are the parameter / buffer storages themselves (no padded or converted copy): the same call refills the
+        # variant after an in-place update (_refill_in_place)
+        if wd.data_ptr() == self.weight.data_ptr() and (firc is None or firc.data_ptr() == fir.data_ptr()):
+            self.__dict__.setdefault('_fill_plans', {})[slot] = (
+                (self.weight.data_ptr(), None if fir is None else fir.data_ptr()),
+                (packed.data_ptr(), None if wsq is None else wsq.data_ptr()), args)
 
     def forward(self, input, style):
         """Module-level call on NCHW fp32 tensors (the fused Generator.forward never goes through here)."""
