@@ -470,6 +470,7 @@ class Generator(nn.Module):
         change; a write through `param.data` does not — call this after one."""
         for layer in self.styled_layers() + self.rgb_layers():
             layer.conv._pack_cache.clear()
+            layer.conv.__dict__.pop('_fill_plans', None)
         self.__dict__.pop('_desc_cache', None)
         self._workspace.clear()
         return self
