@@ -225,7 +225,7 @@ def run_reference(args, rank):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = orc.seeded_state_dict(SIZE, CM, seed=0)
-    sample = BATCH
+    sample = args.ref_frames if args.ref_frames > 0 else BATCH
     step = reference_cpu_problem(sd, sample)
     kind = 'reference'
     if step is None:
@@ -256,7 +256,7 @@ def run_reference(args, rank):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'size': SIZE, 'channel_multiplier': CM,
-                       'sample': '%d frames per step (the full batch of the workload), on the host CPU' % sample},
+                       'sample': '%d frames per step (%s), on the host CPU' % (sample, 'the full batch of the workload' if sample == BATCH else 'a reduced sample: --ref-frames')},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
                              'sample': '%d steps x %d frames, %s' % (args.steps, sample, what)},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -426,6 +426,8 @@ def main():
     ap.add_argument('--cpu-baseline', type=int, default=1)
     ap.add_argument('--gpu-reference', type=int, default=1)
     ap.add_argument('--train', type=int, default=1)
+    ap.add_argument('--ref-frames', type=int, default=0,
+                    help='--impl reference: frames per step (default: the full batch of 32; the CPU contract test uses 2)')
     ap.add_argument('--config', default='256', choices=['256', '1024'],
                     help="256 (default): the headline workload (configs[2] + [3]); 1024: configs[4], the ffhq-1024 bf16 batch sweep")
     args = ap.parse_args()
